@@ -1,0 +1,400 @@
+// See bvh_build.hpp.
+#include "bvh_build.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <thread>
+
+#include "host_math.hpp"
+
+namespace cray {
+
+namespace {
+
+constexpr uint32_t kBuckets = 12;            // bvh.rs:235
+constexpr double kTraversalCost = 1.0 / 8.0; // bvh.rs:236
+constexpr size_t kMaxLeaf = 4;               // bvh.rs:237
+constexpr uint32_t kDeferred = 0xFFFFFFFFu;
+
+struct Item {  // PrimitiveInfo (bvh.rs:149-154); the centroid is recomputed from the box (same expression, same bits)
+    double lo[3], hi[3];
+    uint32_t prim;
+    uint32_t bucket;
+};
+static_assert(sizeof(Item) == 56, "Item layout");
+
+inline Box3 item_box(const Item& it) { return {mk(it.lo[0], it.lo[1], it.lo[2]), mk(it.hi[0], it.hi[1], it.hi[2])}; }
+inline double centroid_axis(const Item& it, int axis) { return (it.lo[axis] + it.hi[axis]) * 0.5; }
+
+struct Accum {  // running Bounds sum, bounds.rs:91-108 / :129-137
+    double lo[3], hi[3];
+    bool some = false;
+    void add(const double* l, const double* h) {
+        if (!some) { std::memcpy(lo, l, 24); std::memcpy(hi, h, 24); some = true; return; }
+        for (int k = 0; k < 3; ++k) { lo[k] = rmin(lo[k], l[k]); hi[k] = rmax(hi[k], h[k]); }
+    }
+    Box3 box() const { return {mk(lo[0], lo[1], lo[2]), mk(hi[0], hi[1], hi[2])}; }
+};
+
+struct SubTree {
+    std::vector<BinNode> nodes;        // local pre-order; deferred placeholders have axis == kDeferred, a = task id
+    std::vector<uint32_t> order;
+    std::string error;
+};
+struct Task {
+    Item* items;
+    size_t n;
+    SubTree tree;
+};
+
+struct Builder {
+    size_t grain;                 // subtrees at or below this size are deferred to the pool (0 = never defer)
+    std::vector<Task>* tasks;
+
+    uint32_t leaf(SubTree& t, const Item* items, size_t n, const Box3& box) {
+        uint32_t idx = (uint32_t)t.nodes.size();
+        t.nodes.push_back({box, (uint32_t)t.order.size(), (uint32_t)n, 3u, 0u});
+        for (size_t i = 0; i < n; ++i) t.order.push_back(items[i].prim);
+        return idx;
+    }
+
+    // BvhNode::from_sah_splitting bvh.rs:234-336
+    uint32_t split(SubTree& t, Item* items, size_t n) {
+        if (grain && n <= grain && tasks) {
+            uint32_t idx = (uint32_t)t.nodes.size();
+            tasks->push_back({items, n, {}});
+            t.nodes.push_back({Box3{}, (uint32_t)tasks->size() - 1, 0u, kDeferred, 0u});
+            return idx;
+        }
+        Accum all, cent;
+        for (size_t i = 0; i < n; ++i) {
+            all.add(items[i].lo, items[i].hi);
+            double c[3] = {centroid_axis(items[i], 0), centroid_axis(items[i], 1), centroid_axis(items[i], 2)};
+            cent.add(c, c);
+        }
+        const Box3 bounds = all.box();
+        if (n <= 1) return leaf(t, items, n, bounds);
+
+        const double total_surface_area = box_surface_area(bounds);
+        if (!(total_surface_area > 0.0)) {
+            if (t.error.empty()) t.error = "Encountered primitives with no surface area";
+            return leaf(t, items, n, bounds);
+        }
+        const Box3 cb = cent.box();
+        const int axis = box_maximum_extent(cb);
+        const double cmin = cb.lo[axis], cext = cb.hi[axis] - cb.lo[axis];
+
+        Accum bucket_box[kBuckets];
+        size_t bucket_count[kBuckets] = {};
+        for (size_t i = 0; i < n; ++i) {
+            const double offset = (centroid_axis(items[i], axis) - cmin) / cext;                 // Bounds::offset bounds.rs:55-61
+            const uint64_t raw = as_usize((double)kBuckets * offset);                             // `as usize`, NaN -> 0
+            const uint32_t b = (uint32_t)std::min<uint64_t>(raw, kBuckets - 1);
+            items[i].bucket = b;
+            bucket_box[b].add(items[i].lo, items[i].hi);
+            bucket_count[b] += 1;
+        }
+        double costs[kBuckets - 1];
+        for (uint32_t i = 0; i + 1 < kBuckets; ++i) {
+            double cost = kTraversalCost;
+            for (int part = 0; part < 2; ++part) {
+                const uint32_t lo = part == 0 ? 0 : i + 1, hi = part == 0 ? i + 1 : kBuckets;
+                Accum merged;
+                size_t count = 0;
+                for (uint32_t k = lo; k < hi; ++k)
+                    if (bucket_box[k].some) { merged.add(bucket_box[k].lo, bucket_box[k].hi); count += bucket_count[k]; }
+                if (merged.some) cost += (double)count * box_surface_area(merged.box()) / total_surface_area;
+            }
+            if (!std::isfinite(cost) && t.error.empty()) t.error = "SAH cost is not finite";
+            costs[i] = cost;
+        }
+        uint32_t best = 0;
+        for (uint32_t i = 0; i + 1 < kBuckets; ++i)
+            if (costs[i] < costs[best]) best = i;
+
+        if ((double)n <= costs[best] && n <= kMaxLeaf) return leaf(t, items, n, bounds);
+
+        // partition_by util.rs:4-26 with pred = bucket <= best
+        size_t left = 0, right = n - 1;
+        while (left != right) {
+            while (left < right && items[left].bucket <= best) left += 1;
+            while (right > left && !(items[right].bucket <= best)) right -= 1;
+            std::swap(items[left], items[right]);
+        }
+        const size_t mid = items[left].bucket <= best ? left + 1 : left;
+        if (mid == 0 || mid == n) {
+            if (t.error.empty()) t.error = "SAH split left one side empty (the reference asserts, bvh.rs:327-328)";
+            return leaf(t, items, n, bounds);
+        }
+        const uint32_t idx = (uint32_t)t.nodes.size();
+        t.nodes.push_back({bounds, 0u, 0u, (uint32_t)axis, 0u});
+        const uint32_t l = split(t, items, mid);
+        const uint32_t right_first = (uint32_t)t.order.size();
+        const uint32_t r = split(t, items + mid, n - mid);
+        t.nodes[idx].a = l;
+        t.nodes[idx].b = r;
+        t.nodes[idx].right_first = right_first;
+        return idx;
+    }
+};
+
+// Splice `src` (local indices / ranks) into the final pre-order arrays.
+void splice(const SubTree& src, const std::vector<Task>& tasks, RefBvh& out) {
+    // iterative DFS over src in pre-order; deferred placeholders expand recursively
+    struct Frame { uint32_t local; uint32_t parent_final; int side; };
+    std::vector<Frame> stack;
+    stack.push_back({0, 0xFFFFFFFFu, 0});
+    while (!stack.empty()) {
+        Frame f = stack.back();
+        stack.pop_back();
+        const BinNode& n = src.nodes[f.local];
+        if (n.axis == kDeferred) {
+            const SubTree& sub = tasks[n.a].tree;
+            const uint32_t node_off = (uint32_t)out.nodes.size(), rank_off = (uint32_t)out.prim_order.size();
+            if (f.parent_final != 0xFFFFFFFFu) {
+                if (f.side == 0) out.nodes[f.parent_final].a = node_off;
+                else { out.nodes[f.parent_final].b = node_off; out.nodes[f.parent_final].right_first = rank_off; }
+            }
+            for (const BinNode& s : sub.nodes) {
+                BinNode c = s;
+                if (c.axis == 3) c.a += rank_off;
+                else { c.a += node_off; c.b += node_off; c.right_first += rank_off; }
+                out.nodes.push_back(c);
+            }
+            out.prim_order.insert(out.prim_order.end(), sub.order.begin(), sub.order.end());
+            if (out.error.empty() && !sub.error.empty()) out.error = sub.error;
+            continue;
+        }
+        const uint32_t me = (uint32_t)out.nodes.size();
+        if (f.parent_final != 0xFFFFFFFFu) {
+            if (f.side == 0) out.nodes[f.parent_final].a = me;
+            else { out.nodes[f.parent_final].b = me; out.nodes[f.parent_final].right_first = (uint32_t)out.prim_order.size(); }
+        }
+        if (n.axis == 3) {
+            BinNode c = n;
+            c.a = (uint32_t)out.prim_order.size();
+            out.nodes.push_back(c);
+            for (uint32_t i = 0; i < n.b; ++i) out.prim_order.push_back(src.order[n.a + i]);
+        } else {
+            out.nodes.push_back(n);
+            // pre-order: left subtree is emitted completely before the right one => push right first
+            stack.push_back({n.b, me, 1});
+            stack.push_back({n.a, me, 0});
+        }
+    }
+}
+
+}  // namespace
+
+Box3 primitive_bounds(const cray_scene_desc& d, uint64_t prim) {  // Shape::bounds shape.rs:402-438
+    const cray_primitive_desc& p = d.primitives[prim];
+    switch (p.shape_kind) {
+        case CRAY_SHAPE_SPHERE: {
+            const cray_sphere_desc& s = d.spheres[p.shape_index];
+            const double r = s.radius;
+            const Xform o2w = xf_translate(s.origin[0], s.origin[1], s.origin[2]);
+            // Bounds::new takes the component-wise min/max of its corners (bounds.rs:16-21)
+            Box3 local{mk(rmin(-r, r), rmin(-r, r), rmin(-r, r)), mk(rmax(-r, r), rmax(-r, r), rmax(-r, r))};
+            return transform_box(o2w.fwd, local);
+        }
+        case CRAY_SHAPE_TRIANGLE: {
+            const cray_triangle_desc& t = d.triangles[p.shape_index];
+            const V3 v0 = mk(t.v0[0], t.v0[1], t.v0[2]);
+            const V3 v1 = v0 + mk(t.e1[0], t.e1[1], t.e1[2]);
+            const V3 v2 = v0 + mk(t.e2[0], t.e2[1], t.e2[2]);
+            return {mk(rmin(v1.x, rmin(v2.x, v0.x)), rmin(v1.y, rmin(v2.y, v0.y)), rmin(v1.z, rmin(v2.z, v0.z))),
+                    mk(rmax(v1.x, rmax(v2.x, v0.x)), rmax(v1.y, rmax(v2.y, v0.y)), rmax(v1.z, rmax(v2.z, v0.z)))};
+        }
+        default: {
+            const cray_disk_desc& k = d.disks[p.shape_index];
+            const double r = k.radius;
+            const Xform o2w = xf_translate(k.origin[0], k.origin[1], k.origin[2]) * xf_rotate(0, to_radians(k.rotate_x)) * xf_rotate(1, to_radians(k.rotate_y));
+            Box3 local{mk(rmin(-r, r), rmin(-r, r), 0.0), mk(rmax(-r, r), rmax(-r, r), 0.0)};
+            return transform_box(o2w.fwd, local);
+        }
+    }
+}
+
+void build_reference_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads) {
+    const size_t n = (size_t)d.n_primitives;
+    out = RefBvh{};
+    if (n == 0) { out.error = "no primitives"; return; }
+    if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+    std::vector<Item> items(n);
+    {
+        // primitive bounds in parallel (pure function of the description)
+        std::vector<std::thread> pool;
+        const size_t chunk = (n + threads - 1) / threads;
+        auto work = [&](size_t b, size_t e) {
+            for (size_t i = b; i < e; ++i) {
+                Box3 bx = primitive_bounds(d, i);
+                items[i] = {{bx.lo.x, bx.lo.y, bx.lo.z}, {bx.hi.x, bx.hi.y, bx.hi.z}, (uint32_t)i, 0u};
+            }
+        };
+        for (unsigned t = 1; t < threads; ++t) {
+            size_t b = t * chunk, e = std::min(n, b + chunk);
+            if (b < e) pool.emplace_back(work, b, e);
+        }
+        work(0, std::min(n, chunk));
+        for (auto& th : pool) th.join();
+    }
+    Accum all;
+    for (size_t i = 0; i < n; ++i) all.add(items[i].lo, items[i].hi);
+    out.bounds = all.box();  // Bvh::bounds bvh.rs:53
+
+    std::vector<Task> tasks;
+    SubTree top;
+    Builder top_builder{(threads > 1 && n > (1u << 16)) ? std::max<size_t>(1u << 14, n / (threads * 16)) : 0, &tasks};
+    top_builder.split(top, items.data(), n);
+    if (!tasks.empty()) {
+        std::atomic<size_t> next{0};
+        auto run = [&]() {
+            Builder b{0, nullptr};
+            for (;;) {
+                size_t i = next.fetch_add(1);
+                if (i >= tasks.size()) break;
+                b.split(tasks[i].tree, tasks[i].items, tasks[i].n);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < threads; ++t) pool.emplace_back(run);
+        run();
+        for (auto& th : pool) th.join();
+    }
+    out.nodes.reserve(2 * n / 3 + 16);
+    out.prim_order.reserve(n);
+    out.error = top.error;
+    splice(top, tasks, out);
+}
+
+// ---- 8-wide collapse ----------------------------------------------------------------------------------
+
+namespace {
+
+float float_down(double x) {
+    float f = (float)x;
+    if ((double)f > x) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+
+struct Collapser {
+    const RefBvh& ref;
+    WideBvh& out;
+    uint32_t max_depth = 0;
+
+    void emit(uint32_t wide_idx, const std::vector<uint32_t>& kids, const Box3& node_box, uint32_t depth) {
+        max_depth = std::max(max_depth, depth);
+        const int k = (int)kids.size();
+        // slot assignment: slot bits (x=4, y=2, z=1) set = child sits on the + side of the node centre on that axis
+        const V3 nc = box_centroid(node_box);
+        double cost[8][8];
+        for (int c = 0; c < k; ++c) {
+            const V3 dc = box_centroid(ref.nodes[kids[c]].box) - nc;
+            for (int s = 0; s < 8; ++s) cost[c][s] = ((s & 4) ? dc.x : -dc.x) + ((s & 2) ? dc.y : -dc.y) + ((s & 1) ? dc.z : -dc.z);
+        }
+        int slot_of[8], child_in[8];
+        for (int i = 0; i < 8; ++i) { slot_of[i] = -1; child_in[i] = -1; }
+        for (int round = 0; round < k; ++round) {
+            int bc = -1, bs = -1;
+            double best = -HUGE_VAL;
+            for (int c = 0; c < k; ++c) {
+                if (slot_of[c] >= 0) continue;
+                for (int s = 0; s < 8; ++s)
+                    if (child_in[s] < 0 && cost[c][s] > best) { best = cost[c][s]; bc = c; bs = s; }
+            }
+            slot_of[bc] = bs;
+            child_in[bs] = bc;
+        }
+        // quantisation frame
+        WideNode w{};
+        const float p[3] = {float_down(node_box.lo.x), float_down(node_box.lo.y), float_down(node_box.lo.z)};
+        w.px = p[0]; w.py = p[1]; w.pz = p[2];
+        int e[3];
+        double scale[3];
+        for (int ax = 0; ax < 3; ++ax) {
+            const double ext = node_box.hi[ax] - (double)p[ax];
+            int ex = -40;
+            if (ext > 0.0) {
+                int fe;
+                std::frexp(ext / 255.0, &fe);  // ext/255 = m * 2^fe, m in [0.5,1)  =>  2^fe >= ext/255
+                ex = fe;
+                while (std::ceil(ext / std::ldexp(1.0, ex)) > 255.0) ex += 1;
+            }
+            ex = std::max(-100, std::min(100, ex));
+            e[ax] = ex;
+            scale[ax] = std::ldexp(1.0, ex);
+        }
+        w.ex = (uint8_t)(e[0] + 127); w.ey = (uint8_t)(e[1] + 127); w.ez = (uint8_t)(e[2] + 127);
+        w.prim_base = (uint32_t)out.prim_order.size();
+        std::vector<uint32_t> interior_kids;
+        uint32_t prim_off = 0;
+        for (int s = 0; s < 8; ++s) {
+            const int c = child_in[s];
+            if (c < 0) { w.meta[s] = 0; continue; }
+            const BinNode& bn = ref.nodes[kids[c]];
+            for (int ax = 0; ax < 3; ++ax) {
+                double ql = std::floor((bn.box.lo[ax] - (double)p[ax]) / scale[ax]);
+                double qh = std::ceil((bn.box.hi[ax] - (double)p[ax]) / scale[ax]);
+                while (ql > 0.0 && (double)p[ax] + ql * scale[ax] > bn.box.lo[ax]) ql -= 1.0;
+                while (qh < 255.0 && (double)p[ax] + qh * scale[ax] < bn.box.hi[ax]) qh += 1.0;
+                ql = std::max(0.0, std::min(255.0, ql));
+                qh = std::max(0.0, std::min(255.0, qh));
+                w.qlo[ax][s] = (uint8_t)ql;
+                w.qhi[ax][s] = (uint8_t)qh;
+            }
+            if (bn.axis == 3) {
+                w.meta[s] = (uint8_t)((bn.b << 5) | prim_off);
+                for (uint32_t i = 0; i < bn.b; ++i) out.prim_order.push_back(ref.prim_order[bn.a + i]);
+                prim_off += bn.b;
+            } else {
+                w.meta[s] = 0xE0;
+                w.imask |= (uint8_t)(1u << s);
+                interior_kids.push_back(kids[c]);
+            }
+        }
+        w.child_base = (uint32_t)out.nodes.size();
+        out.nodes[wide_idx] = w;
+        const uint32_t base = (uint32_t)out.nodes.size();
+        out.nodes.resize(out.nodes.size() + interior_kids.size());
+        for (size_t i = 0; i < interior_kids.size(); ++i) expand(base + (uint32_t)i, interior_kids[i], depth + 1);
+    }
+
+    // Open the binary subtree rooted at interior node `bin` into up to 8 children (largest surface area first).
+    void expand(uint32_t wide_idx, uint32_t bin, uint32_t depth) {
+        std::vector<uint32_t> kids;
+        const BinNode& root = ref.nodes[bin];
+        if (root.axis == 3) kids.push_back(bin);
+        else { kids.push_back(root.a); kids.push_back(root.b); }
+        while (kids.size() < 8) {
+            int pick = -1;
+            double best = -1.0;
+            for (size_t i = 0; i < kids.size(); ++i) {
+                const BinNode& c = ref.nodes[kids[i]];
+                if (c.axis == 3) continue;
+                const double sa = box_surface_area(c.box);
+                if (sa > best) { best = sa; pick = (int)i; }
+            }
+            if (pick < 0) break;
+            const BinNode c = ref.nodes[kids[pick]];
+            kids[pick] = c.a;
+            kids.push_back(c.b);
+        }
+        emit(wide_idx, kids, root.box, depth);
+    }
+};
+
+}  // namespace
+
+void collapse_to_wide(const RefBvh& ref, WideBvh& out) {
+    out = WideBvh{};
+    out.nodes.reserve(ref.nodes.size() / 4 + 16);
+    out.prim_order.reserve(ref.prim_order.size());
+    out.nodes.resize(1);
+    Collapser c{ref, out};
+    c.expand(0, 0, 1);
+    out.depth = c.max_depth;
+}
+
+}  // namespace cray

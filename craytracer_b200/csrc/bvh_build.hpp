@@ -1,0 +1,56 @@
+// Host BVH construction.
+//  * build_reference_bvh: the reference's binned-SAH binary tree (src/bvh.rs:234-336 with src/util.rs
+//    partition_by), reproduced decision-for-decision so that leaf contents, leaf order and split axes
+//    are identical to the reference's -- they define the visit order and therefore which primitive wins
+//    an exact-t tie.  Sub-trees are built by a thread pool (the tree is deterministic, the order of
+//    construction is not observable).
+//  * collapse_to_wide: greedy surface-area collapse of that tree into the GPU's 8-wide node format with
+//    8-bit quantised child boxes (conservatively rounded outward) and octant-ordered child slots.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/cray_b200.h"
+#include "cray_math.cuh"
+
+namespace cray {
+
+struct BinNode {       // 64 B, uploaded as-is for the exact traversal mode
+    Box3 box;          // f64 bounds, bit-identical to the reference's node bounds
+    uint32_t a, b;     // interior: left, right node index (pre-order); leaf: first, count in leaf order
+    uint32_t axis;     // 0..2 split axis, 3 = leaf
+    uint32_t right_first;  // interior: leaf-order rank of the first primitive of the right subtree
+};
+static_assert(sizeof(BinNode) == 64, "BinNode layout");
+
+struct RefBvh {
+    std::vector<BinNode> nodes;        // pre-order, root = 0
+    std::vector<uint32_t> prim_order;  // leaf order -> primitive index
+    Box3 bounds;
+    std::string error;                 // non-empty where the reference would panic (bvh.rs:245, :327-328)
+};
+
+// Bounds of primitive i exactly as Shape::bounds computes them (src/shape.rs:402-438).
+Box3 primitive_bounds(const cray_scene_desc& d, uint64_t prim);
+void build_reference_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads = 0);
+
+struct alignas(16) WideNode {  // 80 B
+    float px, py, pz;          // quantisation frame origin
+    uint8_t ex, ey, ez;        // per-axis scale = 2^(e - 127) (raw f32 exponent field)
+    uint8_t imask;             // bit s: slot s holds an interior child
+    uint32_t child_base;       // first interior child (children contiguous, ascending slot)
+    uint32_t prim_base;        // first leaf primitive of this node in wide leaf order
+    uint8_t meta[8];           // slot: 0 empty | 0xE0 interior | (count 1..4) << 5 | offset (0..28) from prim_base
+    uint8_t qlo[3][8];         // quantised child box minima  [axis][slot]
+    uint8_t qhi[3][8];         // quantised child box maxima
+};
+static_assert(sizeof(WideNode) == 80, "WideNode layout");
+
+struct WideBvh {
+    std::vector<WideNode> nodes;
+    std::vector<uint32_t> prim_order;  // wide leaf order -> primitive index
+    uint32_t depth = 0;
+};
+void collapse_to_wide(const RefBvh& ref, WideBvh& out);
+
+}  // namespace cray

@@ -1,0 +1,90 @@
+// Device-resident scene layout (HBM) shared by all kernels.  See DESIGN.md "Data layout in HBM".
+#pragma once
+#include <cstdint>
+#include "../../include/cray_b200.h"
+#include "bvh_build.hpp"
+#include "cray_math.cuh"
+
+namespace cray {
+
+enum : uint32_t { PRIM_SPHERE = CRAY_SHAPE_SPHERE, PRIM_TRIANGLE = CRAY_SHAPE_TRIANGLE, PRIM_DISK = CRAY_SHAPE_DISK };
+
+// 80-byte intersection record, stored in leaf order so that the <= 4 primitives of a leaf are contiguous.
+//   triangle: d = v0, e1, e2                       (Shape::Triangle, shape.rs:30-33)
+//   sphere  : d[0..2] = origin, d[3] = radius      (object_to_world = translate(origin))
+//   disk    : aux = index into SceneView::disks
+struct alignas(16) LeafPrim {
+    double d[9];
+    uint32_t prim;   // index in reference primitive order
+    uint32_t kind;   // PRIM_* | aux << 8
+};
+static_assert(sizeof(LeafPrim) == 80, "LeafPrim layout");
+
+struct DiskXf {      // Shape::Disk, shape.rs:41-46
+    Affine o2w;      // object_to_world.matrix
+    Affine w2o;      // object_to_world.inverse == world_to_object.matrix
+    double radius, inner_radius;
+};
+
+struct alignas(16) TriShade {  // shading attributes of Shape::Triangle, indexed by shape_index
+    double n0[3], n01[3], n02[3];
+    double uv0[2], uv01[2], uv02[2];
+    double _pad;
+};
+static_assert(sizeof(TriShade) == 128, "TriShade layout");
+
+enum : uint32_t { LOBE_LAMBERTIAN = 0, LOBE_OREN_NAYAR = 1, LOBE_CONDUCTOR = 2, LOBE_SPECULAR_BRDF = 3, LOBE_SPECULAR_BTDF = 4, LOBE_FRESNEL_SPECULAR = 5 };
+
+struct DevLobe {     // BxDF, bxdf.rs:23-50
+    uint32_t kind, _pad;
+    cray_texture_desc t0, t1, sigma;
+    double eta_i, eta_t;
+};
+struct DevMaterial { // Material, material.rs:13-17
+    uint32_t is_bsdf, n_lobes;
+    DevLobe lobes[2];
+};
+struct DevImage {
+    uint32_t width, height;
+    uint64_t offset;  // into SceneView::texels (RGB8)
+};
+struct DevLight {    // Light, light.rs:25-43
+    uint32_t kind;
+    int32_t prim;
+    double v[3];
+    double color[3];
+    LeafPrim shape;  // AREA: the emitting shape (for Shape::sample / pdf_from)
+    double area;     // Shape::area()
+};
+struct DevCamera {   // Camera, camera.rs:15-23
+    double camera_from_raster[4][4];
+    Affine world_from_camera;
+    double lens_radius, focal_distance;
+    uint32_t perspective, width, height, _pad;
+};
+
+struct SceneView {
+    // exact traversal (reference binary BVH)
+    const BinNode* bin_nodes;
+    const LeafPrim* bin_prims;       // reference leaf order
+    // fast traversal (8-wide BVH)
+    const WideNode* wide_nodes;
+    const LeafPrim* wide_prims;      // wide leaf order
+    const uint32_t* rank_of_prim;    // primitive -> rank in the reference leaf order (exact-t tie breaking)
+    const DiskXf* disks;
+    // shading
+    const cray_primitive_desc* prims;
+    const TriShade* tri_shade;
+    const cray_sphere_desc* spheres;
+    const DevMaterial* materials;
+    const DevImage* images;
+    const uint8_t* texels;
+    const double* gamma_lut;         // (c/255)^2.2, c = 0..255 (Color::from_rgb color.rs:39-46)
+    const DevLight* lights;
+    const double* light_cdf;
+    uint32_t n_lights, max_depth;
+    DevCamera camera;
+    Box3 bounds;
+};
+
+}  // namespace cray

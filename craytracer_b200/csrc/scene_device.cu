@@ -1,0 +1,381 @@
+// cray_scene_create / destroy: flatten a cray_scene_desc into the HBM layout of device_types.cuh.
+// Replaces Scene::new (src/scene.rs:25-53): BVH build + LightSampler::new, then one upload.
+#include "scene_device.hpp"
+
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <thread>
+
+#include "host_math.hpp"
+#include "sobol_directions.h"
+
+namespace cray {
+
+namespace {
+thread_local std::string g_error;
+}
+void set_error(const std::string& msg) { g_error = msg; }
+const std::string& last_error() { return g_error; }
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what);
+    return CRAY_E_CUDA;
+}
+
+namespace {
+
+V3 v3(const double* p) { return mk(p[0], p[1], p[2]); }
+
+DiskXf make_disk(const cray_disk_desc& k) {  // Shape::new_disk shape.rs:133-153
+    const Xform o2w = xf_translate(k.origin[0], k.origin[1], k.origin[2]) * xf_rotate(0, to_radians(k.rotate_x)) * xf_rotate(1, to_radians(k.rotate_y));
+    DiskXf d;
+    d.o2w = affine_of(o2w.fwd);
+    d.w2o = affine_of(o2w.inv);
+    d.radius = k.radius;
+    d.inner_radius = k.inner_radius;
+    return d;
+}
+
+LeafPrim make_leaf_prim(const cray_scene_desc& d, uint32_t prim) {
+    const cray_primitive_desc& p = d.primitives[prim];
+    LeafPrim lp{};
+    lp.prim = prim;
+    switch (p.shape_kind) {
+        case CRAY_SHAPE_TRIANGLE: {
+            const cray_triangle_desc& t = d.triangles[p.shape_index];
+            std::memcpy(lp.d, t.v0, 24);
+            std::memcpy(lp.d + 3, t.e1, 24);
+            std::memcpy(lp.d + 6, t.e2, 24);
+            lp.kind = PRIM_TRIANGLE;
+            break;
+        }
+        case CRAY_SHAPE_SPHERE: {
+            const cray_sphere_desc& s = d.spheres[p.shape_index];
+            std::memcpy(lp.d, s.origin, 24);
+            lp.d[3] = s.radius;
+            lp.kind = PRIM_SPHERE;
+            break;
+        }
+        default:
+            lp.kind = PRIM_DISK | (p.shape_index << 8);
+            break;
+    }
+    return lp;
+}
+
+double shape_area(const cray_scene_desc& d, const cray_primitive_desc& p) {  // Shape::area shape.rs:504-514
+    switch (p.shape_kind) {
+        case CRAY_SHAPE_SPHERE: { const double r = d.spheres[p.shape_index].radius; return kPi * (r * r); }
+        case CRAY_SHAPE_TRIANGLE: { const cray_triangle_desc& t = d.triangles[p.shape_index]; return magnitude(cross(v3(t.e1), v3(t.e2))) / 2.0; }
+        default: { const cray_disk_desc& k = d.disks[p.shape_index]; return kPi * (k.radius * k.radius - k.inner_radius * k.inner_radius); }
+    }
+}
+
+bool tex_is_black(const cray_texture_desc& t) {  // texture.rs:82-90
+    auto black = [](const double* c) { return c[0] == 0.0 && c[1] == 0.0 && c[2] == 0.0; };
+    if (t.kind == CRAY_TEX_CONSTANT) return black(t.a);
+    if (t.kind == CRAY_TEX_CHECKERBOARD) return black(t.a) && black(t.b);
+    return false;
+}
+bool tex_is_zero(const cray_texture_desc& t) {  // texture.rs:92-100
+    if (t.kind == CRAY_TEX_CONSTANT) return t.a[0] == 0.0;
+    if (t.kind == CRAY_TEX_CHECKERBOARD) return t.a[0] == 0.0 && t.b[0] == 0.0;
+    return false;
+}
+
+DevMaterial make_material(const cray_material_desc& m) {  // Material::new_* material.rs:20-70
+    DevMaterial r{};
+    auto lobe = [](uint32_t kind, const cray_texture_desc& t0, const cray_texture_desc& t1, const cray_texture_desc& sigma, double eta_i, double eta_t) {
+        DevLobe l{};
+        l.kind = kind; l.t0 = t0; l.t1 = t1; l.sigma = sigma; l.eta_i = eta_i; l.eta_t = eta_t;
+        return l;
+    };
+    switch (m.kind) {
+        case CRAY_MAT_MATTE:
+            r.is_bsdf = 0; r.n_lobes = 1;
+            r.lobes[0] = lobe(tex_is_zero(m.t2) ? LOBE_LAMBERTIAN : LOBE_OREN_NAYAR, m.t0, m.t0, m.t2, 1.0, 1.0);
+            break;
+        case CRAY_MAT_GLASS:
+            r.is_bsdf = 0; r.n_lobes = 1;
+            r.lobes[0] = lobe(LOBE_FRESNEL_SPECULAR, m.t0, m.t1, m.t2, 1.0, m.eta);
+            break;
+        case CRAY_MAT_PLASTIC:
+            r.is_bsdf = 1; r.n_lobes = 0;
+            if (!tex_is_black(m.t0)) r.lobes[r.n_lobes++] = lobe(!tex_is_zero(m.t2) ? LOBE_OREN_NAYAR : LOBE_LAMBERTIAN, m.t0, m.t0, m.t2, 1.0, 1.0);
+            if (!tex_is_black(m.t1)) r.lobes[r.n_lobes++] = lobe(LOBE_SPECULAR_BRDF, m.t1, m.t1, m.t2, 1.0, 1.5);
+            break;
+        default:  // CRAY_MAT_METAL
+            r.is_bsdf = 1; r.n_lobes = 1;
+            r.lobes[0] = lobe(LOBE_CONDUCTOR, m.t0, m.t1, m.t2, 1.0, 1.0);
+            break;
+    }
+    return r;
+}
+
+template <class T>
+int upload(cray_scene* sc, const std::vector<T>& host, const T** dev) {
+    *dev = nullptr;
+    if (host.empty()) return CRAY_OK;
+    void* p = nullptr;
+    CRAY_CUDA(cudaMalloc(&p, host.size() * sizeof(T)));
+    sc->allocations.push_back(p);
+    CRAY_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = static_cast<const T*>(p);
+    return CRAY_OK;
+}
+
+double ms_since(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+int validate(const cray_scene_desc* d) {
+    if (!d) { set_error("null scene description"); return CRAY_E_INVALID; }
+    if (d->n_primitives == 0) { set_error("scene has no primitives"); return CRAY_E_INVALID; }
+    if (d->n_lights == 0) { set_error("No lights in the scene."); return CRAY_E_INVALID; }  // scene_parser.rs:1103
+    if (d->n_primitives >= 0xFFFFFFF0ull) { set_error("too many primitives"); return CRAY_E_INVALID; }
+    if (d->camera.width == 0 || d->camera.height == 0 || d->camera.width > 65535 || d->camera.height > 65535) { set_error("film size out of range"); return CRAY_E_INVALID; }
+    for (uint64_t i = 0; i < d->n_primitives; ++i) {
+        const cray_primitive_desc& p = d->primitives[i];
+        const uint64_t lim = p.shape_kind == CRAY_SHAPE_SPHERE ? d->n_spheres : (p.shape_kind == CRAY_SHAPE_TRIANGLE ? d->n_triangles : (p.shape_kind == CRAY_SHAPE_DISK ? d->n_disks : 0));
+        if (p.shape_index >= lim) { set_error("primitive references a missing shape"); return CRAY_E_INVALID; }
+        if (p.area_light >= 0) {
+            if ((uint64_t)p.area_light >= d->n_lights || d->lights[p.area_light].kind != CRAY_LIGHT_AREA) { set_error("Non area light provided as area light for shape"); return CRAY_E_INVALID; }
+        } else if (p.material < 0 || (uint64_t)p.material >= d->n_materials) { set_error("primitive references a missing material"); return CRAY_E_INVALID; }
+    }
+    for (uint64_t i = 0; i < d->n_lights; ++i)
+        if (d->lights[i].kind == CRAY_LIGHT_AREA && (d->lights[i].primitive < 0 || (uint64_t)d->lights[i].primitive >= d->n_primitives)) { set_error("area light references a missing primitive"); return CRAY_E_INVALID; }
+    for (uint64_t i = 0; i < d->n_materials; ++i) {
+        const cray_texture_desc* ts[3] = {&d->materials[i].t0, &d->materials[i].t1, &d->materials[i].t2};
+        for (auto* t : ts)
+            if (t->kind == CRAY_TEX_IMAGE && (t->image < 0 || (uint64_t)t->image >= d->n_images)) { set_error("texture references a missing image"); return CRAY_E_INVALID; }
+    }
+    return CRAY_OK;
+}
+
+}  // namespace
+}  // namespace cray
+
+using namespace cray;
+
+extern "C" {
+
+const char* cray_last_error(void) { return cray::last_error().c_str(); }
+const char* cray_version(void) { return "craytracer_b200 0.1 (sm_100a)"; }
+void cray_free(void* p) { std::free(p); }
+
+int cray_build_reference_bvh(const cray_scene_desc* desc, cray_bvh_node_dump** nodes, uint64_t* n_nodes, uint32_t** prim_order, uint64_t* n_prims) {
+    if (!desc || desc->n_primitives == 0 || !nodes || !n_nodes || !prim_order || !n_prims) { set_error("bad arguments"); return CRAY_E_INVALID; }
+    RefBvh bvh;
+    build_reference_bvh(*desc, bvh);
+    if (!bvh.error.empty()) { set_error(bvh.error); return CRAY_E_BVH; }
+    auto* out = (cray_bvh_node_dump*)std::malloc(sizeof(cray_bvh_node_dump) * bvh.nodes.size());
+    auto* order = (uint32_t*)std::malloc(sizeof(uint32_t) * bvh.prim_order.size());
+    for (size_t i = 0; i < bvh.nodes.size(); ++i) {
+        const BinNode& n = bvh.nodes[i];
+        out[i] = {{n.box.lo.x, n.box.lo.y, n.box.lo.z}, {n.box.hi.x, n.box.hi.y, n.box.hi.z}, n.axis, n.a, n.b, 0};
+    }
+    std::memcpy(order, bvh.prim_order.data(), sizeof(uint32_t) * bvh.prim_order.size());
+    *nodes = out; *n_nodes = bvh.nodes.size();
+    *prim_order = order; *n_prims = bvh.prim_order.size();
+    return CRAY_OK;
+}
+
+void cray_scene_destroy(cray_scene* sc) {
+    if (!sc) return;
+    cudaSetDevice(sc->device);
+    extern void cray_pool_release(cray_scene*);
+    cray_pool_release(sc);
+    for (void* p : sc->allocations) cudaFree(p);
+    if (sc->stream) cudaStreamDestroy(sc->stream);
+    delete sc;
+}
+
+int cray_scene_create(const cray_scene_desc* d, int device, uint32_t build_flags, cray_scene** out) {
+    if (!out) { set_error("null output handle"); return CRAY_E_INVALID; }
+    *out = nullptr;
+    int rc = validate(d);
+    if (rc != CRAY_OK) return rc;
+    if (build_flags == 0) build_flags = CRAY_BUILD_EXACT | CRAY_BUILD_FAST;
+    build_flags |= CRAY_BUILD_EXACT;  // the binary tree also resolves exact-t ties for the fast mode
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { set_error("no CUDA device available (this library has no CPU fallback)"); return CRAY_E_CUDA; }
+    if (device < 0 || device >= count) { set_error("CUDA device index out of range"); return CRAY_E_INVALID; }
+    CRAY_CUDA(cudaSetDevice(device));
+
+    auto t0 = std::chrono::steady_clock::now();
+    RefBvh ref;
+    build_reference_bvh(*d, ref);
+    if (!ref.error.empty()) { set_error(ref.error); return CRAY_E_BVH; }
+    WideBvh wide;
+    if (build_flags & CRAY_BUILD_FAST) {
+        collapse_to_wide(ref, wide);
+        if (wide.depth >= (uint32_t)30) { set_error("wide BVH deeper than the traversal stack"); return CRAY_E_BVH; }
+    }
+    const double build_ms = ms_since(t0);
+    t0 = std::chrono::steady_clock::now();
+
+    auto sc = new cray_scene();
+    sc->device = device;
+    sc->build_flags = build_flags;
+    struct Guard { cray_scene* s; ~Guard() { if (s) cray_scene_destroy(s); } } guard{sc};
+    CRAY_CUDA(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
+
+    const size_t np = (size_t)d->n_primitives;
+    // leaf-ordered intersection records
+    std::vector<LeafPrim> bin_prims(np), wide_prims(wide.prim_order.size());
+    std::vector<uint32_t> rank_of_prim(np);
+    {
+        const unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+        std::vector<std::thread> pool;
+        auto work = [&](unsigned t) {
+            for (size_t i = t; i < np; i += nt) {
+                bin_prims[i] = make_leaf_prim(*d, ref.prim_order[i]);
+                rank_of_prim[ref.prim_order[i]] = (uint32_t)i;
+                if (!wide_prims.empty()) wide_prims[i] = make_leaf_prim(*d, wide.prim_order[i]);
+            }
+        };
+        for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (auto& th : pool) th.join();
+    }
+    std::vector<DiskXf> disks(d->n_disks);
+    for (size_t i = 0; i < disks.size(); ++i) disks[i] = make_disk(d->disks[i]);
+    std::vector<TriShade> tri_shade(d->n_triangles);
+    for (size_t i = 0; i < tri_shade.size(); ++i) {
+        const cray_triangle_desc& t = d->triangles[i];
+        TriShade& ts = tri_shade[i];
+        std::memcpy(ts.n0, t.n0, 24); std::memcpy(ts.n01, t.n01, 24); std::memcpy(ts.n02, t.n02, 24);
+        std::memcpy(ts.uv0, t.uv0, 16); std::memcpy(ts.uv01, t.uv01, 16); std::memcpy(ts.uv02, t.uv02, 16);
+        ts._pad = 0.0;
+    }
+    // materials (+ the black matte that area-light primitives carry, primitive.rs:43-46)
+    std::vector<DevMaterial> materials(d->n_materials + 1);
+    for (size_t i = 0; i < d->n_materials; ++i) materials[i] = make_material(d->materials[i]);
+    {
+        cray_material_desc black{};
+        black.kind = CRAY_MAT_MATTE;
+        black.t0.kind = black.t1.kind = black.t2.kind = CRAY_TEX_CONSTANT;
+        materials[d->n_materials] = make_material(black);
+    }
+    std::vector<cray_primitive_desc> prims(d->primitives, d->primitives + np);
+    for (auto& p : prims)
+        if (p.area_light >= 0) p.material = (int32_t)d->n_materials;
+    // images
+    std::vector<DevImage> images(d->n_images);
+    std::vector<uint8_t> texels;
+    for (size_t i = 0; i < images.size(); ++i) {
+        images[i] = {d->images[i].width, d->images[i].height, (uint64_t)texels.size()};
+        const size_t bytes = (size_t)d->images[i].width * d->images[i].height * 3;
+        texels.insert(texels.end(), d->images[i].rgb, d->images[i].rgb + bytes);
+    }
+    std::vector<double> gamma_lut(256);
+    for (int c = 0; c < 256; ++c) gamma_lut[c] = std::pow((double)c / 255.0, 2.2);  // Color::from_rgb color.rs:39-46
+    // lights + LightSampler::new (light.rs:187-199); world radius = half the BVH diagonal (scene.rs:42)
+    const double world_radius = magnitude(ref.bounds.hi - ref.bounds.lo) * 0.5;
+    std::vector<DevLight> lights(d->n_lights);
+    std::vector<double> cdf(d->n_lights);
+    double total_power = 0.0;
+    for (size_t i = 0; i < lights.size(); ++i) {
+        const cray_light_desc& l = d->lights[i];
+        DevLight dl{};
+        dl.kind = l.kind;
+        dl.prim = l.primitive;
+        std::memcpy(dl.v, l.v, 24);
+        std::memcpy(dl.color, l.color, 24);
+        Color3 c = mkc(l.color[0], l.color[1], l.color[2]), power;
+        switch (l.kind) {  // Light::power light.rs:170-177
+            case CRAY_LIGHT_POINT: power = c * 4.0 * kPi; break;
+            case CRAY_LIGHT_DISTANT:
+            case CRAY_LIGHT_INFINITE: power = c * kPi * world_radius * world_radius; break;
+            default:
+                dl.shape = make_leaf_prim(*d, (uint32_t)l.primitive);
+                dl.area = shape_area(*d, d->primitives[l.primitive]);
+                power = c * kPi * dl.area;
+                break;
+        }
+        const double power_avg = (power.r + power.g + power.b) / 3.0;
+        total_power += power_avg;
+        cdf[i] = total_power;
+        lights[i] = dl;
+    }
+    for (double& c : cdf) c = c / total_power;
+    // camera (camera.rs:55-129)
+    DevCamera cam{};
+    {
+        const cray_camera_desc& c = d->camera;
+        const Xform wfc = xf_look_at(v3(c.origin), v3(c.target), v3(c.up));
+        const Xform sfc = c.kind == CRAY_CAMERA_PERSPECTIVE ? xf_perspective(c.fov, 1e-2, 1000.0) : xf_orthographic(0.0, 1.0);
+        const Xform cfr = camera_from_raster(sfc, c.width);
+        std::memcpy(cam.camera_from_raster, cfr.fwd.m, sizeof(cam.camera_from_raster));
+        cam.world_from_camera = affine_of(wfc.fwd);
+        cam.lens_radius = c.lens_radius;
+        cam.focal_distance = c.focal_distance;
+        cam.perspective = c.kind == CRAY_CAMERA_PERSPECTIVE;
+        cam.width = c.width;
+        cam.height = c.height;
+    }
+    // pixel order: 8 x 4 pixel tiles (one warp = one tile), tiles row-major
+    std::vector<uint32_t> pixel_order;
+    pixel_order.reserve((size_t)cam.width * cam.height);
+    for (uint32_t ty = 0; ty < cam.height; ty += 4)
+        for (uint32_t tx = 0; tx < cam.width; tx += 8)
+            for (uint32_t y = ty; y < std::min(ty + 4, cam.height); ++y)
+                for (uint32_t x = tx; x < std::min(tx + 8, cam.width); ++x) pixel_order.push_back(x | (y << 16));
+    std::vector<uint32_t> sobol(&SOBOL_DIRECTIONS_INIT[0][0], &SOBOL_DIRECTIONS_INIT[0][0] + 256 * 32);
+
+    SceneView& v = sc->view;
+    const uint32_t* d_order = nullptr;
+    const uint32_t* d_sobol = nullptr;
+    std::vector<cray_sphere_desc> spheres(d->spheres, d->spheres + d->n_spheres);
+#define UP(vec, field) do { rc = upload(sc, vec, &field); if (rc != CRAY_OK) return rc; } while (0)
+    UP(ref.nodes, v.bin_nodes);
+    UP(bin_prims, v.bin_prims);
+    UP(wide.nodes, v.wide_nodes);
+    UP(wide_prims, v.wide_prims);
+    UP(rank_of_prim, v.rank_of_prim);
+    UP(disks, v.disks);
+    UP(prims, v.prims);
+    UP(tri_shade, v.tri_shade);
+    UP(spheres, v.spheres);
+    UP(materials, v.materials);
+    UP(images, v.images);
+    UP(texels, v.texels);
+    UP(gamma_lut, v.gamma_lut);
+    UP(lights, v.lights);
+    UP(cdf, v.light_cdf);
+    UP(pixel_order, d_order);
+    UP(sobol, d_sobol);
+#undef UP
+    sc->d_pixel_order = const_cast<uint32_t*>(d_order);
+    sc->d_sobol = const_cast<uint32_t*>(d_sobol);
+    v.n_lights = (uint32_t)d->n_lights;
+    v.max_depth = d->max_depth;
+    v.camera = cam;
+    v.bounds = ref.bounds;
+    CRAY_CUDA(cudaDeviceSynchronize());
+
+    cray_scene_info& info = sc->info;
+    info.n_primitives = np;
+    info.n_lights = d->n_lights;
+    info.exact_nodes = ref.nodes.size();
+    info.exact_bytes = ref.nodes.size() * sizeof(BinNode);
+    info.wide_nodes = wide.nodes.size();
+    info.wide_bytes = wide.nodes.size() * sizeof(WideNode);
+    info.leaf_prim_bytes = np * sizeof(LeafPrim);
+    info.wide_depth = wide.depth;
+    info.width = cam.width; info.height = cam.height;
+    info.max_depth = d->max_depth; info.num_samples = d->num_samples;
+    info.bvh_build_ms = build_ms;
+    info.upload_ms = ms_since(t0);
+    guard.s = nullptr;
+    *out = sc;
+    return CRAY_OK;
+}
+
+int cray_scene_get_info(const cray_scene* sc, cray_scene_info* out) {
+    if (!sc || !out) { set_error("bad arguments"); return CRAY_E_INVALID; }
+    *out = sc->info;
+    return CRAY_OK;
+}
+
+}  // extern "C"

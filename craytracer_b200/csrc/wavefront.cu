@@ -1,0 +1,647 @@
+// Kernels and entry points of the hot path.
+//
+//   S3  cray_trace_closest / cray_trace_any     one thread per ray, exact or wide traversal
+//   S2  cray_estimate_li                         the wavefront below on an explicit (x, y, sample) list
+//   S1  cray_render                              the wavefront below on every (pixel, sample) of a sample range
+//
+// Wavefront pipeline (replaces render / render_tile / render_pixel / estimate_Li, src/bin/craytracer.rs:148-291 and
+// src/path_integrator.rs:41-215): a pool of path slots lives in HBM as structure-of-arrays; every iteration runs
+//   k_generate  flush finished paths into the film, refill their slots with new camera rays (sampler + camera)
+//   k_extend    closest-hit traversal of every live path's ray
+//   k_shade     one path vertex: emission, light sample + shadow ray, BSDF sample, Russian roulette
+//   k_shadow    any-hit traversal of the shadow rays, adds the unoccluded light contributions
+// so all lanes keep working until the sample range is exhausted (path regeneration).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "scene_device.hpp"
+#include "shading.cuh"
+#include "traverse.cuh"
+
+namespace cray {
+
+enum : uint32_t { SLOT_EMPTY = 0, SLOT_ACTIVE = 1, SLOT_DONE = 2 };
+
+struct Pool {  // structure-of-arrays over `capacity` path slots
+    uint32_t capacity;
+    double *ox, *oy, *oz, *dx, *dy, *dz;          // ray to extend (max_distance is always +inf: Ray::new)
+    double *hit_t, *hit_u, *hit_v;                 // result of k_extend
+    uint32_t* hit_slot;
+    double *beta_r, *beta_g, *beta_b, *L_r, *L_g, *L_b, *prev_bsdf_pdf;
+    double *sdx, *sdy, *sdz, *smax, *sc_r, *sc_g, *sc_b;  // pending shadow ray (origin = ox,oy,oz) and its contribution
+    uint32_t *id, *pixel, *hash, *shuffled_rev;    // job-relative sample id, film offset, sampler state
+    uint32_t* state;                               // state | bounces << 8 | specular << 16 | shadow_pending << 17 | bad << 18
+};
+
+struct Job {
+    uint64_t seed;
+    uint64_t n_total;           // samples in this job
+    uint32_t sample_begin;
+    uint32_t n_pixels;
+    const uint32_t* pixel_order;  // full frame: id -> sample sample_begin + id / n_pixels of pixel pixel_order[id % n_pixels]
+    const uint32_t *lx, *ly, *ls; // explicit list (S2), or null
+    double* film;               // W*H*3 f64 sums, or null
+    double* out_rgb;            // per-sample radiance (S2), or null
+    const uint32_t* sobol;
+    int exact;                  // traversal mode
+};
+
+struct Counters {
+    unsigned long long next_id;
+    unsigned long long live;         // ACTIVE slots after the last k_generate
+    unsigned long long closest_rays, shadow_rays, nan_samples;
+};
+
+__device__ __forceinline__ uint32_t st_state(uint32_t s) { return s & 0xFFu; }
+__device__ __forceinline__ uint32_t st_bounces(uint32_t s) { return (s >> 8) & 0xFFu; }
+
+template <bool ANY>
+__device__ __forceinline__ bool trace(const SceneView& s, int exact, V3 o, V3 d, double ray_max, Hit& hit) {
+    if (exact) return traverse_exact<ANY>(s, o, d, ray_max, hit);
+    return traverse_wide<ANY>(s, o, d, ray_max, hit);
+}
+
+// ---- S3 kernels ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128) k_trace_closest(SceneView s, int exact, const cray_ray* __restrict__ rays, uint64_t n, cray_hit* __restrict__ hits,
+                                                        cray_surface* __restrict__ surf) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const cray_ray r = rays[i];
+    const V3 o = mk(r.origin[0], r.origin[1], r.origin[2]), d = mk(r.direction[0], r.direction[1], r.direction[2]);
+    Hit h;
+    cray_hit out;
+    out._pad = 0;
+    if (trace<false>(s, exact, o, d, r.max_distance, h)) {
+        const LeafPrim lp = load_leaf_prim((exact ? s.bin_prims : s.wide_prims) + h.slot);
+        V3 loc, nrm;
+        double tu, tv;
+        // spheres / disks accept in object space and may report ray.max_distance instead of t (primitive.rs:65);
+        // their surface point is always at the accepted root, which equals h.t whenever max_distance > EPSILON
+        surface_at(s, lp, o, d, h.t, h.u, h.v, loc, nrm, tu, tv);
+        const bool tri = (lp.kind & 0xFFu) == PRIM_TRIANGLE;
+        out.prim = lp.prim;
+        out.t = h.t;
+        out.u = tri ? h.u : tu;
+        out.v = tri ? h.v : tv;
+        if (surf) {
+            cray_surface sf;
+            sf.location[0] = loc.x; sf.location[1] = loc.y; sf.location[2] = loc.z;
+            sf.normal[0] = nrm.x; sf.normal[1] = nrm.y; sf.normal[2] = nrm.z;
+            sf.uv[0] = tu; sf.uv[1] = tv;
+            surf[i] = sf;
+        }
+    } else {
+        out.prim = CRAY_NO_HIT;
+        out.t = 0.0; out.u = 0.0; out.v = 0.0;
+        if (surf) {
+            cray_surface sf;
+            memset(&sf, 0, sizeof(sf));
+            surf[i] = sf;
+        }
+    }
+    hits[i] = out;
+}
+
+__global__ void __launch_bounds__(128) k_trace_any(SceneView s, int exact, const cray_ray* __restrict__ rays, uint64_t n, uint8_t* __restrict__ occluded) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const cray_ray r = rays[i];
+    Hit h;
+    occluded[i] = trace<true>(s, exact, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), r.max_distance, h) ? 1 : 0;
+}
+
+// ---- wavefront kernels --------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void warp_count(unsigned long long* counter, bool pred) {
+    const unsigned mask = __ballot_sync(__activemask(), pred);
+    if (pred && (threadIdx.x & 31) == (unsigned)(__ffs(mask) - 1)) atomicAdd(counter, (unsigned long long)__popc(mask));
+}
+
+// Camera::sample + generate_ray camera.rs:131-162
+__device__ __forceinline__ void camera_ray(const DevCamera& c, double fu, double fv, double lu, double lv, uint32_t x, uint32_t y, V3& o, V3& d) {
+    const double dx = 2.0 * fu - 1.0, dy = 2.0 * fv - 1.0;
+    const V3 pr = mk((double)x + dx, (double)y + dy, 0.0);
+    const double(*m)[4] = c.camera_from_raster;
+    V3 pc = mk(m[0][0] * pr.x + m[0][1] * pr.y + m[0][2] * pr.z + m[0][3], m[1][0] * pr.x + m[1][1] * pr.y + m[1][2] * pr.z + m[1][3],
+               m[2][0] * pr.x + m[2][1] * pr.y + m[2][2] * pr.z + m[2][3]);
+    pc = pc / (m[3][0] * pr.x + m[3][1] * pr.y + m[3][2] * pr.z + m[3][3]);
+    V3 ro = pc, rd = c.perspective ? normalized(pc - mk(0.0, 0.0, 0.0)) : mk(0.0, 0.0, 1.0);
+    if (c.lens_radius != 0.0) {
+        const double lens_x = 2.0 * lu - 1.0, lens_y = 2.0 * lv - 1.0;
+        const V3 p_lens = mk(lens_x * c.lens_radius, lens_y * c.lens_radius, 0.0);
+        const V3 p_focal = ro + rd * (c.focal_distance / rd.z);
+        ro = p_lens;
+        rd = normalized(p_focal - p_lens);
+    }
+    o = xf_point(c.world_from_camera, ro);
+    d = xf_vector(c.world_from_camera, rd);
+}
+
+__global__ void __launch_bounds__(256) k_generate(SceneView s, Pool p, Job job, Counters* counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.capacity) return;
+    uint32_t st = p.state[i];
+    if (st_state(st) == SLOT_DONE) {
+        // flush: craytracer.rs:177-188 accumulates the sample into its pixel; a sample on which the reference would
+        // have panicked (path_integrator.rs:208-209 and the asserts of its callees) is dropped and counted
+        const double r = p.L_r[i], g = p.L_g[i], b = p.L_b[i];
+        const bool bad = ((st >> 18) & 1u) || !(isfinite(r) && isfinite(g) && isfinite(b));
+        if (bad) {
+            atomicAdd(&counters->nan_samples, 1ull);
+        } else if (job.film) {
+            double* px = job.film + 3ull * p.pixel[i];
+            atomicAdd(px, r); atomicAdd(px + 1, g); atomicAdd(px + 2, b);
+        }
+        if (job.out_rgb) {
+            double* dst = job.out_rgb + 3ull * p.id[i];
+            dst[0] = r; dst[1] = g; dst[2] = b;
+        }
+        st = SLOT_EMPTY;
+    }
+    if (st_state(st) == SLOT_EMPTY) {
+        // claim the next sample id (warp-aggregated)
+        const unsigned mask = __activemask();
+        const unsigned lane = threadIdx.x & 31;
+        const unsigned leader = __ffs(mask) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(&counters->next_id, (unsigned long long)__popc(mask));
+        base = __shfl_sync(mask, base, leader);
+        const unsigned long long id = base + __popc(mask & ((1u << lane) - 1u));
+        if (id < job.n_total) {
+            uint32_t x, y, si;
+            if (job.lx) { x = job.lx[id]; y = job.ly[id]; si = job.ls[id]; }
+            else {
+                const uint32_t po = job.pixel_order[id % job.n_pixels];
+                x = po & 0xFFFFu; y = po >> 16;
+                si = job.sample_begin + (uint32_t)(id / job.n_pixels);
+            }
+            PixelSampler smp;
+            smp.start_pixel(job.seed, x, y, si);
+            const double fu = smp.sample_1d(job.sobol), fv = smp.sample_1d(job.sobol);
+            const double lu = smp.sample_1d(job.sobol), lv = smp.sample_1d(job.sobol);
+            V3 o, d;
+            camera_ray(s.camera, fu, fv, lu, lv, x, y, o, d);
+            p.ox[i] = o.x; p.oy[i] = o.y; p.oz[i] = o.z;
+            p.dx[i] = d.x; p.dy[i] = d.y; p.dz[i] = d.z;
+            p.beta_r[i] = 1.0; p.beta_g[i] = 1.0; p.beta_b[i] = 1.0;
+            p.L_r[i] = 0.0; p.L_g[i] = 0.0; p.L_b[i] = 0.0;
+            p.prev_bsdf_pdf[i] = 0.0;
+            p.id[i] = (uint32_t)id;
+            p.pixel[i] = x + y * s.camera.width;
+            p.hash[i] = smp.hash;
+            p.shuffled_rev[i] = smp.shuffled_rev;
+            st = SLOT_ACTIVE | (1u << 16);  // bounces = 0, is_specular_bounce = true (path_integrator.rs:50)
+        }
+    }
+    p.state[i] = st;
+    warp_count(&counters->live, st_state(st) == SLOT_ACTIVE);
+}
+
+__global__ void __launch_bounds__(128) k_extend(SceneView s, Pool p, Job job, Counters* counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.capacity) return;
+    const bool active = st_state(p.state[i]) == SLOT_ACTIVE;
+    warp_count(&counters->closest_rays, active);
+    if (!active) return;
+    Hit h;
+    trace<false>(s, job.exact, mk(p.ox[i], p.oy[i], p.oz[i]), mk(p.dx[i], p.dy[i], p.dz[i]), inf_f64(), h);
+    p.hit_slot[i] = h.slot;
+    p.hit_t[i] = h.t; p.hit_u[i] = h.u; p.hit_v[i] = h.v;
+}
+
+// One iteration of the `while` loop of estimate_Li (path_integrator.rs:54-212) for one path.
+__global__ void __launch_bounds__(128) k_shade(SceneView s, Pool p, Job job, Counters* counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.capacity) return;
+    uint32_t st = p.state[i];
+    if (st_state(st) != SLOT_ACTIVE) return;
+    const uint32_t bounces = st_bounces(st);
+    const bool is_specular_bounce = (st >> 16) & 1u;
+    bool bad = (st >> 18) & 1u;
+    const V3 ro = mk(p.ox[i], p.oy[i], p.oz[i]), rd = mk(p.dx[i], p.dy[i], p.dz[i]);
+    const V3 w_o = neg(rd);
+    Color3 L = mkc(p.L_r[i], p.L_g[i], p.L_b[i]);
+    Color3 beta = mkc(p.beta_r[i], p.beta_g[i], p.beta_b[i]);
+    const double prev_bsdf_pdf = p.prev_bsdf_pdf[i];
+    const uint32_t slot = p.hit_slot[i];
+
+    auto finish = [&](Color3 Lf, bool shadow_pending) {
+        p.L_r[i] = Lf.r; p.L_g[i] = Lf.g; p.L_b[i] = Lf.b;
+        p.state[i] = SLOT_DONE | (bounces << 8) | ((shadow_pending ? 1u : 0u) << 17) | ((bad ? 1u : 0u) << 18);
+    };
+
+    if (slot == CRAY_NO_HIT) {  // path_integrator.rs:60-90
+        for (uint32_t li = 0; li < s.n_lights; ++li) {
+            const DevLight& light = s.lights[li];
+            if (light.kind != CRAY_LIGHT_INFINITE) continue;  // Light::Le is black for every other kind (light.rs:161-168)
+            const Color3 Le = mkc(light.color[0], light.color[1], light.color[2]);
+            if (is_specular_bounce) {
+                L = L + beta * Le;
+            } else if (!is_black(Le)) {
+                const double light_pdf = (kFrac1Pi / 4.0) * light_pick_pdf(s, li);
+                const double weight = power_heuristic(light_pdf, prev_bsdf_pdf);
+                L = L + beta * Le * weight;
+            }
+        }
+        finish(L, false);
+        return;
+    }
+
+    const LeafPrim lp = load_leaf_prim((job.exact ? s.bin_prims : s.wide_prims) + slot);
+    V3 location, normal;
+    double tu, tv;
+    surface_at(s, lp, ro, rd, p.hit_t[i], p.hit_u[i], p.hit_v[i], location, normal, tu, tv);
+    const cray_primitive_desc prim = s.prims[lp.prim];
+    const DevMaterial& material = s.materials[prim.material];
+
+    // PathSegmentSamples::from path_integrator.rs:25-36 -- dimensions 4 + 8 * bounces ...
+    PixelSampler smp;
+    smp.hash = p.hash[i];
+    smp.shuffled_rev = p.shuffled_rev[i];
+    smp.dimension = 4u + 8u * bounces;
+    const double mat_1d = smp.sample_1d(job.sobol);
+    const double mat_u = smp.sample_1d(job.sobol), mat_v = smp.sample_1d(job.sobol);
+    const double light_index_1d = smp.sample_1d(job.sobol);
+    const double light_1d = smp.sample_1d(job.sobol);
+    const double light_u = smp.sample_1d(job.sobol), light_v = smp.sample_1d(job.sobol);
+    const double rr_1d = smp.sample_1d(job.sobol);
+
+    // emission (:106-126)
+    if (prim.area_light >= 0) {
+        const DevLight& light = s.lights[prim.area_light];
+        const Color3 Le = mkc(light.color[0], light.color[1], light.color[2]);
+        if (!is_black(Le)) {
+            if (is_specular_bounce) {
+                L = L + beta * Le;
+            } else {
+                const double light_pdf = light_pdf_li(s, light, location, normal, w_o).value * light_pick_pdf(s, (uint32_t)prim.area_light);
+                const double weight = power_heuristic(light_pdf, prev_bsdf_pdf);
+                L = L + beta * Le * weight;
+            }
+        }
+    }
+
+    // next-event estimation (:129-164): the shadow ray is traced by k_shadow, the contribution is parked
+    bool shadow_pending = false;
+    {
+        double light_sampler_pdf;
+        const uint32_t light_index = light_pick(s, light_index_1d, light_sampler_pdf);
+        const DevLight& light = s.lights[light_index];
+        const LightSample ls = light_sample_li(s, light, light_1d, light_u, light_v, location, normal, bad);
+        Color3 contribution = mkc(0.0, 0.0, 0.0);
+        const Color3 f = material_f(s, material, w_o, ls.w_i, normal, tu, tv);
+        const double cos_theta = fabs(dot(ls.w_i, normal));
+        if (!ls.pdf.delta) {
+            if (ls.pdf.value > 0.0) {
+                const double light_pdf = ls.pdf.value * light_sampler_pdf;
+                const PdfValue bp = material_pdf(material, w_o, ls.w_i, normal);
+                const double bsdf_pdf = bp.delta ? 0.0 : bp.value;
+                const double weight = power_heuristic(light_pdf, bsdf_pdf);
+                contribution = beta * ls.Li * f * cos_theta * weight / light_pdf;
+            }
+        } else {
+            contribution = beta * ls.Li * f * cos_theta / light_sampler_pdf;
+        }
+        // the reference always casts the shadow ray (:141); it is counted as a ray here too, but only traced when
+        // an unoccluded result could change L
+        warp_count(&counters->shadow_rays, true);
+        if (!is_black(contribution) || !is_finite3(contribution)) {
+            shadow_pending = true;
+            p.sdx[i] = ls.w_i.x; p.sdy[i] = ls.w_i.y; p.sdz[i] = ls.w_i.z;
+            p.smax[i] = ls.shadow_max;
+            p.sc_r[i] = contribution.r; p.sc_g[i] = contribution.g; p.sc_b[i] = contribution.b;
+        }
+    }
+    // shadow ray and continuation ray both start at the hit location (no offset, :191)
+    p.ox[i] = location.x; p.oy[i] = location.y; p.oz[i] = location.z;
+
+    // BSDF sample (:167-195)
+    SurfaceSample ss;
+    if (!material_sample(s, material, mat_1d, mat_u, mat_v, w_o, normal, tu, tv, ss, bad)) { finish(L, shadow_pending); return; }
+    if (is_black(ss.f)) { finish(L, shadow_pending); return; }
+    const double cos_theta = fabs(dot(ss.w_i, normal));
+    const double bsdf_pdf = ss.pdf.delta ? 1.0 : ss.pdf.value;
+    if (bsdf_pdf == 0.0) { finish(L, shadow_pending); return; }
+    beta = beta * ss.f * cos_theta / bsdf_pdf;
+
+    // Russian roulette (:197-206)
+    if (bounces > 0) {
+        const double max_beta_component = rmax(beta.r, rmax(beta.g, beta.b));
+        if (max_beta_component < 1.0) {
+            const double q = 1.0 - max_beta_component;
+            if (rr_1d < q) { finish(L, shadow_pending); return; }
+            beta = beta / (1.0 - q);
+        }
+    }
+    // assert!(L.is_finite()); assert!(beta.is_finite()) (:208-209).  L still lacks this vertex's light sample, which
+    // k_shadow adds; k_generate re-checks L when the path is flushed.
+    if (!is_finite3(L) || !is_finite3(beta)) { bad = true; finish(L, shadow_pending); return; }
+
+    const uint32_t next_bounces = bounces + 1;
+    p.L_r[i] = L.r; p.L_g[i] = L.g; p.L_b[i] = L.b;
+    if (next_bounces < s.max_depth && !is_black(beta)) {  // loop condition (:54)
+        p.dx[i] = ss.w_i.x; p.dy[i] = ss.w_i.y; p.dz[i] = ss.w_i.z;
+        p.beta_r[i] = beta.r; p.beta_g[i] = beta.g; p.beta_b[i] = beta.b;
+        p.prev_bsdf_pdf[i] = bsdf_pdf;
+        p.state[i] = SLOT_ACTIVE | (next_bounces << 8) | ((ss.is_specular ? 1u : 0u) << 16) | ((shadow_pending ? 1u : 0u) << 17) | ((bad ? 1u : 0u) << 18);
+    } else {
+        p.state[i] = SLOT_DONE | (next_bounces << 8) | ((shadow_pending ? 1u : 0u) << 17) | ((bad ? 1u : 0u) << 18);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_shadow(SceneView s, Pool p, Job job) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.capacity) return;
+    const uint32_t st = p.state[i];
+    if (!((st >> 17) & 1u)) return;
+    p.state[i] = st & ~(1u << 17);
+    Hit h;
+    if (!trace<true>(s, job.exact, mk(p.ox[i], p.oy[i], p.oz[i]), mk(p.sdx[i], p.sdy[i], p.sdz[i]), p.smax[i], h)) {
+        p.L_r[i] += p.sc_r[i]; p.L_g[i] += p.sc_g[i]; p.L_b[i] += p.sc_b[i];
+    }
+}
+
+__global__ void k_film_to_f32(const double* __restrict__ film, float* __restrict__ out, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)film[i];
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+
+struct PoolStorage {
+    Pool pool{};
+    void* slab = nullptr;
+    Counters* d_counters = nullptr;
+    Counters* h_counters = nullptr;  // pinned
+    double* d_film = nullptr;
+    uint64_t film_elems = 0;
+};
+
+int ensure_pool(cray_scene* sc, uint32_t capacity) {
+    auto* ps = static_cast<PoolStorage*>(sc->pool);
+    if (!ps) { ps = new PoolStorage(); sc->pool = ps; }
+    if (ps->pool.capacity >= capacity) return CRAY_OK;
+    if (ps->slab) { cudaFree(ps->slab); ps->slab = nullptr; }
+    const size_t n = capacity;
+    const size_t n_f64 = 24, n_u32 = 6;
+    const size_t bytes = n * (n_f64 * 8 + n_u32 * 4);
+    CRAY_CUDA(cudaMalloc(&ps->slab, bytes));
+    CRAY_CUDA(cudaMemsetAsync(ps->slab, 0, bytes, sc->stream));
+    double* f = static_cast<double*>(ps->slab);
+    Pool& p = ps->pool;
+    double** fields[] = {&p.ox, &p.oy, &p.oz, &p.dx, &p.dy, &p.dz, &p.hit_t, &p.hit_u, &p.hit_v, &p.beta_r, &p.beta_g, &p.beta_b,
+                         &p.L_r, &p.L_g, &p.L_b, &p.prev_bsdf_pdf, &p.sdx, &p.sdy, &p.sdz, &p.smax, &p.sc_r, &p.sc_g, &p.sc_b};
+    size_t k = 0;
+    for (double** fp : fields) { *fp = f + k * n; ++k; }
+    uint32_t* u = reinterpret_cast<uint32_t*>(f + n_f64 * n);
+    uint32_t** ufields[] = {&p.hit_slot, &p.id, &p.pixel, &p.hash, &p.shuffled_rev, &p.state};
+    k = 0;
+    for (uint32_t** up : ufields) { *up = u + k * n; ++k; }
+    p.capacity = capacity;
+    if (!ps->d_counters) {
+        CRAY_CUDA(cudaMalloc(&ps->d_counters, sizeof(Counters)));
+        CRAY_CUDA(cudaMallocHost(&ps->h_counters, sizeof(Counters)));
+    }
+    return CRAY_OK;
+}
+
+// Runs the wavefront until every sample of `job` has been flushed.
+int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t stream, cray_render_stats* stats) {
+    int rc = ensure_pool(sc, capacity);
+    if (rc != CRAY_OK) return rc;
+    auto* ps = static_cast<PoolStorage*>(sc->pool);
+    Pool pool = ps->pool;
+    pool.capacity = capacity;
+    CRAY_CUDA(cudaMemsetAsync(pool.state, 0, sizeof(uint32_t) * capacity, stream));
+    CRAY_CUDA(cudaMemsetAsync(ps->d_counters, 0, sizeof(Counters), stream));
+    cudaEvent_t e0, e1, t0, t1;
+    CRAY_CUDA(cudaEventCreate(&e0)); CRAY_CUDA(cudaEventCreate(&e1));
+    CRAY_CUDA(cudaEventCreate(&t0)); CRAY_CUDA(cudaEventCreate(&t1));
+    CRAY_CUDA(cudaEventRecord(e0, stream));
+    const unsigned g256 = (capacity + 255) / 256, g128 = (capacity + 127) / 128;
+    uint64_t iterations = 0, launches = 0;
+    double trace_ms = 0.0;
+    for (;;) {
+        CRAY_CUDA(cudaMemsetAsync(&ps->d_counters->live, 0, sizeof(unsigned long long), stream));
+        k_generate<<<g256, 256, 0, stream>>>(sc->view, pool, job, ps->d_counters);
+        CRAY_CUDA(cudaMemcpyAsync(ps->h_counters, ps->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+        CRAY_CUDA(cudaStreamSynchronize(stream));
+        launches += 1;
+        if (ps->h_counters->live == 0) break;
+        const bool timed = stats != nullptr;
+        if (timed) CRAY_CUDA(cudaEventRecord(t0, stream));
+        k_extend<<<g128, 128, 0, stream>>>(sc->view, pool, job, ps->d_counters);
+        if (timed) CRAY_CUDA(cudaEventRecord(t1, stream));
+        k_shade<<<g128, 128, 0, stream>>>(sc->view, pool, job, ps->d_counters);
+        k_shadow<<<g128, 128, 0, stream>>>(sc->view, pool, job);
+        launches += 3;
+        iterations += 1;
+        if (timed) {
+            CRAY_CUDA(cudaEventSynchronize(t1));
+            float ms = 0;
+            CRAY_CUDA(cudaEventElapsedTime(&ms, t0, t1));
+            trace_ms += ms;
+        }
+    }
+    CRAY_CUDA(cudaEventRecord(e1, stream));
+    CRAY_CUDA(cudaEventSynchronize(e1));
+    CRAY_CUDA(cudaGetLastError());
+    float ms = 0;
+    CRAY_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (stats) {
+        stats->samples = job.n_total;
+        stats->closest_rays = ps->h_counters->closest_rays;
+        stats->shadow_rays = ps->h_counters->shadow_rays;
+        stats->nan_samples = ps->h_counters->nan_samples;
+        stats->iterations = iterations;
+        stats->kernel_launches = launches;
+        stats->render_ms = ms;
+        stats->trace_ms = trace_ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(t0); cudaEventDestroy(t1);
+    return CRAY_OK;
+}
+
+int check_mode(const cray_scene* sc, int mode) {
+    if (!sc) { set_error("null scene"); return CRAY_E_INVALID; }
+    if (mode != CRAY_TRAVERSE_EXACT && mode != CRAY_TRAVERSE_FAST) { set_error("unknown traversal mode"); return CRAY_E_INVALID; }
+    if (mode == CRAY_TRAVERSE_FAST && !(sc->build_flags & CRAY_BUILD_FAST)) { set_error("scene was created without CRAY_BUILD_FAST"); return CRAY_E_INVALID; }
+    return CRAY_OK;
+}
+
+}  // namespace cray
+
+using namespace cray;
+
+extern "C" {
+
+void cray_pool_release(cray_scene* sc) {
+    auto* ps = static_cast<PoolStorage*>(sc->pool);
+    if (!ps) return;
+    if (ps->slab) cudaFree(ps->slab);
+    if (ps->d_counters) cudaFree(ps->d_counters);
+    if (ps->h_counters) cudaFreeHost(ps->h_counters);
+    if (ps->d_film) cudaFree(ps->d_film);
+    delete ps;
+    sc->pool = nullptr;
+}
+
+int cray_trace_closest_device(cray_scene* sc, int mode, const cray_ray* d_rays, uint64_t n, cray_hit* d_hits, cray_surface* d_surf, void* stream) {
+    int rc = check_mode(sc, mode);
+    if (rc != CRAY_OK) return rc;
+    if (n == 0) return CRAY_OK;
+    if (!d_rays || !d_hits) { set_error("null buffer"); return CRAY_E_INVALID; }
+    CRAY_CUDA(cudaSetDevice(sc->device));
+    const uint64_t blocks = (n + 127) / 128;
+    k_trace_closest<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(sc->view, mode == CRAY_TRAVERSE_EXACT, d_rays, n, d_hits, d_surf);
+    CRAY_CUDA(cudaGetLastError());
+    return CRAY_OK;
+}
+
+int cray_trace_any_device(cray_scene* sc, int mode, const cray_ray* d_rays, uint64_t n, uint8_t* d_occluded, void* stream) {
+    int rc = check_mode(sc, mode);
+    if (rc != CRAY_OK) return rc;
+    if (n == 0) return CRAY_OK;
+    if (!d_rays || !d_occluded) { set_error("null buffer"); return CRAY_E_INVALID; }
+    CRAY_CUDA(cudaSetDevice(sc->device));
+    const uint64_t blocks = (n + 127) / 128;
+    k_trace_any<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(sc->view, mode == CRAY_TRAVERSE_EXACT, d_rays, n, d_occluded);
+    CRAY_CUDA(cudaGetLastError());
+    return CRAY_OK;
+}
+
+int cray_trace_closest(cray_scene* sc, int mode, const cray_ray* rays, uint64_t n, cray_hit* hits, cray_surface* surf) {
+    int rc = check_mode(sc, mode);
+    if (rc != CRAY_OK) return rc;
+    if (n == 0) return CRAY_OK;
+    if (!rays || !hits) { set_error("null buffer"); return CRAY_E_INVALID; }
+    CRAY_CUDA(cudaSetDevice(sc->device));
+    cray_ray* d_rays = nullptr;
+    cray_hit* d_hits = nullptr;
+    cray_surface* d_surf = nullptr;
+    CRAY_CUDA(cudaMalloc(&d_rays, n * sizeof(cray_ray)));
+    cudaError_t e = cudaMalloc(&d_hits, n * sizeof(cray_hit));
+    if (e == cudaSuccess && surf) e = cudaMalloc(&d_surf, n * sizeof(cray_surface));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, n * sizeof(cray_ray), cudaMemcpyHostToDevice, sc->stream);
+    if (e == cudaSuccess) {
+        rc = cray_trace_closest_device(sc, mode, d_rays, n, d_hits, d_surf, sc->stream);
+        if (rc == CRAY_OK) e = cudaMemcpyAsync(hits, d_hits, n * sizeof(cray_hit), cudaMemcpyDeviceToHost, sc->stream);
+        if (rc == CRAY_OK && e == cudaSuccess && surf) e = cudaMemcpyAsync(surf, d_surf, n * sizeof(cray_surface), cudaMemcpyDeviceToHost, sc->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(sc->stream);
+    }
+    cudaFree(d_rays); cudaFree(d_hits); cudaFree(d_surf);
+    if (e != cudaSuccess) return cuda_fail(e, "cray_trace_closest");
+    return rc;
+}
+
+int cray_trace_any(cray_scene* sc, int mode, const cray_ray* rays, uint64_t n, uint8_t* occluded) {
+    int rc = check_mode(sc, mode);
+    if (rc != CRAY_OK) return rc;
+    if (n == 0) return CRAY_OK;
+    if (!rays || !occluded) { set_error("null buffer"); return CRAY_E_INVALID; }
+    CRAY_CUDA(cudaSetDevice(sc->device));
+    cray_ray* d_rays = nullptr;
+    uint8_t* d_occ = nullptr;
+    CRAY_CUDA(cudaMalloc(&d_rays, n * sizeof(cray_ray)));
+    cudaError_t e = cudaMalloc(&d_occ, n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, n * sizeof(cray_ray), cudaMemcpyHostToDevice, sc->stream);
+    if (e == cudaSuccess) {
+        rc = cray_trace_any_device(sc, mode, d_rays, n, d_occ, sc->stream);
+        if (rc == CRAY_OK) e = cudaMemcpyAsync(occluded, d_occ, n, cudaMemcpyDeviceToHost, sc->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(sc->stream);
+    }
+    cudaFree(d_rays); cudaFree(d_occ);
+    if (e != cudaSuccess) return cuda_fail(e, "cray_trace_any");
+    return rc;
+}
+
+int cray_estimate_li(cray_scene* sc, int mode, uint64_t seed, const uint32_t* x, const uint32_t* y, const uint32_t* sample_index, uint64_t n, double* rgb) {
+    int rc = check_mode(sc, mode);
+    if (rc != CRAY_OK) return rc;
+    if (n == 0) return CRAY_OK;
+    if (!x || !y || !sample_index || !rgb) { set_error("null buffer"); return CRAY_E_INVALID; }
+    if (n > 0xFFFFFFFFull) { set_error("too many samples in one call"); return CRAY_E_INVALID; }
+    CRAY_CUDA(cudaSetDevice(sc->device));
+    uint32_t* d_list = nullptr;
+    double* d_rgb = nullptr;
+    CRAY_CUDA(cudaMalloc(&d_list, 3 * n * sizeof(uint32_t)));
+    cudaError_t e = cudaMalloc(&d_rgb, 3 * n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_list, x, n * 4, cudaMemcpyHostToDevice, sc->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_list + n, y, n * 4, cudaMemcpyHostToDevice, sc->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_list + 2 * n, sample_index, n * 4, cudaMemcpyHostToDevice, sc->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_rgb, 0, 3 * n * sizeof(double), sc->stream);
+    if (e == cudaSuccess) {
+        Job job{};
+        job.seed = seed; job.n_total = n;
+        job.lx = d_list; job.ly = d_list + n; job.ls = d_list + 2 * n;
+        job.out_rgb = d_rgb;
+        job.sobol = sc->d_sobol;
+        job.exact = mode == CRAY_TRAVERSE_EXACT;
+        const uint32_t capacity = (uint32_t)std::min<uint64_t>(n, 1u << 20);
+        rc = run_wavefront(sc, job, capacity, sc->stream, nullptr);
+        if (rc == CRAY_OK) e = cudaMemcpy(rgb, d_rgb, 3 * n * sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_list); cudaFree(d_rgb);
+    if (e != cudaSuccess) return cuda_fail(e, "cray_estimate_li");
+    return rc;
+}
+
+int cray_render_device(cray_scene* sc, int mode, uint64_t seed, uint32_t sample_begin, uint32_t sample_end, float* d_rgb_sum, void* stream_, cray_render_stats* stats) {
+    int rc = check_mode(sc, mode);
+    if (rc != CRAY_OK) return rc;
+    if (!d_rgb_sum || sample_end < sample_begin) { set_error("bad arguments"); return CRAY_E_INVALID; }
+    if (sample_end > 65536u) { set_error("sample index beyond the sampler's 2^16 points (sobol_burley uses 16 index bits)"); return CRAY_E_INVALID; }
+    CRAY_CUDA(cudaSetDevice(sc->device));
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : sc->stream;
+    const uint64_t n_pixels = (uint64_t)sc->info.width * sc->info.height;
+    const uint64_t n_total = n_pixels * (sample_end - sample_begin);
+    if (n_total > 0xFFFFFFFFull) { set_error("more than 2^32 samples in one call: split the sample range"); return CRAY_E_INVALID; }
+    rc = ensure_pool(sc, 1);
+    if (rc != CRAY_OK) return rc;
+    auto* ps = static_cast<PoolStorage*>(sc->pool);
+    if (ps->film_elems < n_pixels * 3) {
+        if (ps->d_film) cudaFree(ps->d_film);
+        CRAY_CUDA(cudaMalloc(&ps->d_film, n_pixels * 3 * sizeof(double)));
+        ps->film_elems = n_pixels * 3;
+    }
+    CRAY_CUDA(cudaMemsetAsync(ps->d_film, 0, n_pixels * 3 * sizeof(double), stream));
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (n_total > 0) {
+        Job job{};
+        job.seed = seed; job.n_total = n_total;
+        job.sample_begin = sample_begin;
+        job.n_pixels = (uint32_t)n_pixels;
+        job.pixel_order = sc->d_pixel_order;
+        job.film = ps->d_film;
+        job.sobol = sc->d_sobol;
+        job.exact = mode == CRAY_TRAVERSE_EXACT;
+        const uint32_t capacity = (uint32_t)std::min<uint64_t>(n_total, 1u << 21);
+        rc = run_wavefront(sc, job, capacity, stream, stats);
+        if (rc != CRAY_OK) return rc;
+    }
+    k_film_to_f32<<<(unsigned)((n_pixels * 3 + 255) / 256), 256, 0, stream>>>(ps->d_film, d_rgb_sum, n_pixels * 3);
+    if (stats) stats->kernel_launches += 1;
+    CRAY_CUDA(cudaStreamSynchronize(stream));
+    CRAY_CUDA(cudaGetLastError());
+    return CRAY_OK;
+}
+
+int cray_render(cray_scene* sc, int mode, uint64_t seed, uint32_t sample_begin, uint32_t sample_end, float* rgb_sum, cray_render_stats* stats) {
+    if (!sc || !rgb_sum) { set_error("bad arguments"); return CRAY_E_INVALID; }
+    CRAY_CUDA(cudaSetDevice(sc->device));
+    const uint64_t n = (uint64_t)sc->info.width * sc->info.height * 3;
+    float* d_out = nullptr;
+    CRAY_CUDA(cudaMalloc(&d_out, n * sizeof(float)));
+    int rc = cray_render_device(sc, mode, seed, sample_begin, sample_end, d_out, sc->stream, stats);
+    cudaError_t e = cudaSuccess;
+    if (rc == CRAY_OK) e = cudaMemcpy(rgb_sum, d_out, n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return cuda_fail(e, "cray_render");
+    return rc;
+}
+
+}  // extern "C"
