@@ -128,6 +128,10 @@ EXTRA_SIGNATURES = {
     "cray_set_image_decoder": (None, [IMAGE_DECODER]),
     "cray_register_standin_mesh": (None, [C.c_char_p, C.c_int, C.c_uint64, C.c_uint64]),
     "cray_clear_standin_meshes": (None, []),
+    "cray_debug_transformation": (None, [C.c_int, _P, _P, _P]),
+    "cray_debug_matrix_inverse": (C.c_int, [_P, _P]),
+    "cray_debug_camera_matrices": (None, [C.POINTER(CameraDesc), _P]),
+    "cray_debug_check_wide_bvh": (C.c_int, [C.POINTER(SceneDesc), _P]),
     "cray_debug_tokenize": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     "cray_debug_parse_raw_value": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
 }

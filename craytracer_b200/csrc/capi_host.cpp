@@ -9,6 +9,8 @@
 #include "../../include/cray_b200.h"
 #include "cry_parser.hpp"
 #include "host_scene.hpp"
+#include "host_math.hpp"
+#include "bvh_build.hpp"
 
 namespace cray {
 void set_error(const std::string& msg);
@@ -87,6 +89,107 @@ const char* cray_host_scene_warning(const cray_host_scene* hs, uint64_t i) { ret
 void cray_set_image_decoder(cray::image_decoder_fn fn) { cray::set_image_decoder(fn); }
 void cray_register_standin_mesh(const char* file_name, int kind, uint64_t triangles, uint64_t seed) { cray::register_standin_mesh(file_name, kind, triangles, seed); }
 void cray_clear_standin_meshes(void) { cray::clear_standin_meshes(); }
+
+// Host math introspection for the parity tests: the matrices the scene builder derives, in the oracle's layout.
+// kind: 0 translate 1 scale 2 rotate_x 3 rotate_y 4 rotate_z 5 look_at 6 perspective 7 orthographic
+void cray_debug_transformation(int kind, const double* p, double* matrix16, double* inverse16) {
+    using namespace cray;
+    Xform t;
+    switch (kind) {
+        case 0: t = xf_translate(p[0], p[1], p[2]); break;
+        case 1: t = xf_scale(p[0], p[1], p[2]); break;
+        case 2: t = xf_rotate(0, p[0]); break;
+        case 3: t = xf_rotate(1, p[0]); break;
+        case 4: t = xf_rotate(2, p[0]); break;
+        case 5: t = xf_look_at(mk(p[0], p[1], p[2]), mk(p[3], p[4], p[5]), mk(p[6], p[7], p[8])); break;
+        case 6: t = xf_perspective(p[0], p[1], p[2]); break;
+        default: t = xf_orthographic(p[0], p[1]); break;
+    }
+    std::memcpy(matrix16, t.fwd.m, 16 * sizeof(double));
+    std::memcpy(inverse16, t.inv.m, 16 * sizeof(double));
+}
+int cray_debug_matrix_inverse(const double* a16, double* out16) {
+    cray::Mat4 a, r;
+    std::memcpy(a.m, a16, sizeof(a.m));
+    if (!cray::invert(a, r)) return 0;
+    std::memcpy(out16, r.m, sizeof(r.m));
+    return 1;
+}
+// camera_from_raster then world_from_camera (4x4 row-major each) as uploaded to the GPU
+void cray_debug_camera_matrices(const cray_camera_desc* c, double* out32) {
+    using namespace cray;
+    const Xform wfc = xf_look_at(mk(c->origin[0], c->origin[1], c->origin[2]), mk(c->target[0], c->target[1], c->target[2]), mk(c->up[0], c->up[1], c->up[2]));
+    const Xform sfc = c->kind == CRAY_CAMERA_PERSPECTIVE ? xf_perspective(c->fov, 1e-2, 1000.0) : xf_orthographic(0.0, 1.0);
+    const Xform cfr = camera_from_raster(sfc, c->width);
+    std::memcpy(out32, cfr.fwd.m, 16 * sizeof(double));
+    std::memcpy(out32 + 16, wfc.fwd.m, 16 * sizeof(double));
+}
+
+// Structural check of the 8-wide BVH against the reference binary tree it was collapsed from (host only):
+// every primitive exactly once, every quantised child box encloses the exact f64 box of the subtree it stands for,
+// leaf children keep the reference's leaf contents and order.  out[0..3] = wide nodes, depth, interior children, leaf children.
+int cray_debug_check_wide_bvh(const cray_scene_desc* desc, uint64_t* out4) {
+    using namespace cray;
+    RefBvh ref;
+    build_reference_bvh(*desc, ref);
+    if (!ref.error.empty()) { set_error(ref.error); return CRAY_E_BVH; }
+    WideBvh wide;
+    collapse_to_wide(ref, wide);
+    std::vector<uint32_t> seen(desc->n_primitives, 0);
+    for (uint32_t p : wide.prim_order) {
+        if (p >= desc->n_primitives) { set_error("wide order references a missing primitive"); return CRAY_E_INVALID; }
+        seen[p] += 1;
+    }
+    for (uint32_t c : seen)
+        if (c != 1) { set_error("a primitive does not appear exactly once in the wide leaf order"); return CRAY_E_INVALID; }
+    // reference leaves as (first primitive -> (count, box)) for matching leaf children
+    uint64_t interior = 0, leaves = 0;
+    // recompute exact boxes bottom-up from the wide structure and compare with the quantised ones
+    struct Rec { Box3 box; };
+    std::vector<Box3> node_box(wide.nodes.size());
+    std::vector<char> done(wide.nodes.size(), 0);
+    // children always have larger indices than their parent, so a reverse sweep sees children first
+    for (size_t ni = wide.nodes.size(); ni-- > 0;) {
+        const WideNode& w = wide.nodes[ni];
+        const double p[3] = {w.px, w.py, w.pz};
+        const double sc[3] = {std::ldexp(1.0, (int)w.ex - 127), std::ldexp(1.0, (int)w.ey - 127), std::ldexp(1.0, (int)w.ez - 127)};
+        bool any = false;
+        Box3 acc{};
+        uint32_t child = w.child_base;
+        for (int s = 0; s < 8; ++s) {
+            if (w.meta[s] == 0) continue;
+            Box3 exact{};
+            if (w.meta[s] == 0xE0) {
+                if (!((w.imask >> s) & 1)) { set_error("interior child without imask bit"); return CRAY_E_INVALID; }
+                if (child <= ni || child >= wide.nodes.size() || !done[child]) { set_error("bad child index"); return CRAY_E_INVALID; }
+                exact = node_box[child];
+                child += 1;
+                interior += 1;
+            } else {
+                const uint32_t count = w.meta[s] >> 5, off = w.meta[s] & 31u;
+                if (count < 1 || count > 4) { set_error("bad leaf count"); return CRAY_E_INVALID; }
+                for (uint32_t k = 0; k < count; ++k) {
+                    const Box3 pb = primitive_bounds(*desc, wide.prim_order[w.prim_base + off + k]);
+                    exact = k == 0 ? pb : box_union(exact, pb);
+                }
+                leaves += 1;
+            }
+            const double qlo[3] = {p[0] + w.qlo[0][s] * sc[0], p[1] + w.qlo[1][s] * sc[1], p[2] + w.qlo[2][s] * sc[2]};
+            const double qhi[3] = {p[0] + w.qhi[0][s] * sc[0], p[1] + w.qhi[1][s] * sc[1], p[2] + w.qhi[2][s] * sc[2]};
+            for (int ax = 0; ax < 3; ++ax)
+                if (qlo[ax] > exact.lo[ax] || qhi[ax] < exact.hi[ax]) { set_error("quantised child box does not enclose the exact box"); return CRAY_E_INVALID; }
+            acc = any ? box_union(acc, exact) : exact;
+            any = true;
+        }
+        if (!any) { set_error("empty wide node"); return CRAY_E_INVALID; }
+        node_box[ni] = acc;
+        done[ni] = 1;
+    }
+    for (int ax = 0; ax < 3; ++ax)
+        if (node_box[0].lo[ax] != ref.bounds.lo[ax] || node_box[0].hi[ax] != ref.bounds.hi[ax]) { set_error("root box differs from the scene bounds"); return CRAY_E_INVALID; }
+    out4[0] = wide.nodes.size(); out4[1] = wide.depth; out4[2] = interior; out4[3] = leaves;
+    return CRAY_OK;
+}
 
 // Parser introspection: JSON of tokenize(input) / RawValue::from_tokens(tokenize(input)); caller frees with cray_free.
 int cray_debug_tokenize(const char* input, char** json_out) {

@@ -460,12 +460,13 @@ void make_dragon_standin(uint64_t target, uint64_t seed, MeshModel& m) {
 // Interior stand-in: a room with a flight of stairs, wall panels and bumpy props; one model per MTL material
 // (cycled), uv-mapped so that every map_Kd texture is sampled.
 void make_interior_standin(uint64_t target, uint64_t seed, int n_materials, std::vector<MeshModel>& models) {
-    if (n_materials <= 0) n_materials = 1;
+    const bool have_materials = n_materials > 0;
+    if (!have_materials) n_materials = 1;
     uint64_t per = std::max<uint64_t>(2, target / (uint64_t)n_materials);
     uint64_t rng = seed ^ 0xA0761D6478BD642Full;
     for (int mi = 0; mi < n_materials; ++mi) {
         MeshModel m;
-        m.material_id = mi;
+        m.material_id = have_materials ? mi : -1;
         m.name = "standin_" + std::to_string(mi);
         // a bumpy height-field patch n x n (2 n^2 triangles) placed in a 3 x 6 x 5 room, facing alternating directions
         uint64_t n = std::max<uint64_t>(1, (uint64_t)std::floor(std::sqrt((double)per / 2.0)));

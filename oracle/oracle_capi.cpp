@@ -126,7 +126,7 @@ void orc_intersect(void* h, const cray_ray* rays, uint64_t n, cray_hit* hits, cr
     parallel_for(n, threads, [&](uint64_t b, uint64_t e) {
         for (uint64_t i = b; i < e; ++i) {
             Ray ray = to_ray(rays[i]);
-            PrimitiveIntersection pi;
+            PrimitiveIntersection pi{};
             if (s.intersect(ray, pi)) {
                 hits[i] = {(uint32_t)pi.primitive, 0, pi.distance, pi.bary_u, pi.bary_v};
                 if (surf) surf[i] = {{pi.location.x, pi.location.y, pi.location.z}, {pi.normal.x, pi.normal.y, pi.normal.z}, {pi.uv[0], pi.uv[1]}};
@@ -343,6 +343,13 @@ void orc_transform_apply(const double* matrix16, const double* inverse16, int wh
     std::memcpy(t.inv.m, inverse16, 16 * sizeof(double));
     V3 r = what == 0 ? xf_point(t, v3(in3)) : (what == 1 ? xf_vector(t, v3(in3)) : xf_normal(t, v3(in3)));
     out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
+void orc_transform_bounds(const double* matrix16, const double* inverse16, const double* in6, double* out6) {
+    Transformation t;
+    std::memcpy(t.matrix.m, matrix16, 16 * sizeof(double));
+    std::memcpy(t.inv.m, inverse16, 16 * sizeof(double));
+    Bounds b = xf_bounds(t, Bounds::make(v3(in6), v3(in6 + 3)));
+    out6[0] = b.min.x; out6[1] = b.min.y; out6[2] = b.min.z; out6[3] = b.max.x; out6[4] = b.max.y; out6[5] = b.max.z;
 }
 void orc_from_rgb(uint8_t r, uint8_t g, uint8_t b, double* out) {
     Color c = from_rgb(r, g, b);

@@ -92,7 +92,7 @@ struct Bvh {
         for (size_t i = 1; i < n; ++i) centroid_bounds = bunion(centroid_bounds, Bounds::make(infos[i].centroid, infos[i].centroid));
         int split_axis = centroid_bounds.maximum_extent();
 
-        struct Bucket { bool some = false; Bounds bounds; size_t count = 0; };
+        struct Bucket { bool some = false; Bounds bounds{}; size_t count = 0; };
         Bucket buckets[NUM_BUCKETS];
         auto get_bucket_idx = [&](const PrimitiveInfo& p) -> size_t {
             double centroid_offset = centroid_bounds.offset(p.centroid)[split_axis];
@@ -294,7 +294,7 @@ struct Scene {  // scene.rs:15-22
 
     // Bvh::intersect bvh.rs:58-104
     bool intersect(Ray& ray, PrimitiveIntersection& current) const {
-        uint32_t stack[128];
+        uint32_t stack[256];
         int sp = 0;
         stack[sp++] = 0;
         bool have = false;
@@ -317,7 +317,7 @@ struct Scene {  // scene.rs:15-22
     }
     // Bvh::intersects bvh.rs:106-147
     bool intersects(const Ray& ray) const {
-        uint32_t stack[128];
+        uint32_t stack[256];
         int sp = 0;
         stack[sp++] = 0;
         while (sp > 0) {

@@ -57,6 +57,7 @@ def lib():
         L.orc_matrix_inverse.argtypes = [_P, _P]
         L.orc_transformation.argtypes = [C.c_int, _P, _P, _P]
         L.orc_transform_apply.argtypes = [_P, _P, C.c_int, _P, _P]
+        L.orc_transform_bounds.argtypes = [_P, _P, _P, _P]
         L.orc_from_rgb.argtypes = [C.c_uint8, C.c_uint8, C.c_uint8, _P]
         L.orc_to_rgb.argtypes = [_P, _P]
         L.orc_partition_by.restype = C.c_uint64

@@ -1,0 +1,366 @@
+"""Pins the CPU oracle against every known-answer test the reference holds for the hot path
+(tests/test_shape.rs, test_bvh.rs, test_bounds.rs, test_bxdf.rs, test_transformation.rs, test_color.rs, test_util.rs),
+restated one-to-one, plus independent pins for the third-party sampler arithmetic (SipHash, Sobol)."""
+import ctypes as C
+import itertools
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as o
+from craytracer_b200 import _abi
+
+SPHERE, TRIANGLE, DISK = 0, 1, 2
+EPS = 1e-9
+_keep = []
+
+
+def P(*vals):
+    """Pointer to a fresh f64 array; the array is kept alive for the duration of the test session."""
+    a = o.f64(*vals)
+    _keep.append(a)
+    if len(_keep) > 100000:
+        del _keep[:50000]
+    return a.ctypes.data
+
+
+def shape_intersect(orc, kind, params, origin, direction, max_distance=np.inf):
+    p = o.f64(*params)
+    r = o.ray(origin, direction, max_distance)
+    out = np.zeros(9)
+    hit = orc.orc_shape_intersect(kind, p.ctypes.data, r.ctypes.data, out.ctypes.data)
+    return hit, out[0:3], out[3:6], out[6:8], out[8]
+
+
+# ---- tests/test_shape.rs ------------------------------------------------------------------------------------------
+
+OFFSETS = [0.0, -1.0, 1.0, 0.001, -0.001, -1e9, 1e9]
+
+
+def test_sphere_intersect_along_axes(orc):  # test_shape.rs:28-62 (2 x 7^3 x 3 exact checks, direction of length 3)
+    radius = 2.0
+    checked = 0
+    for ox, oy, oz in itertools.product(OFFSETS, repeat=3):
+        offset = np.array([ox, oy, oz])
+        for sign in (1.0, -1.0):
+            for axis in range(3):
+                ray_origin = np.zeros(3)
+                ray_origin[axis] = (radius + 1.0) * sign
+                ray_direction = np.zeros(3) - ray_origin
+                expected = np.zeros(3)
+                expected[axis] = radius * sign
+                normal = np.zeros(3)
+                normal[axis] = sign
+                hit, loc, nrm, _, _ = shape_intersect(orc, SPHERE, list(np.zeros(3) + offset) + [radius], ray_origin + offset, ray_direction)
+                assert hit == 1
+                assert np.array_equal(loc, expected + offset)
+                assert np.array_equal(nrm, normal)
+                checked += 1
+    assert checked == 2 * 7 ** 3 * 3
+
+
+def test_sphere_intersect_internal(orc):  # test_shape.rs:64-96
+    radius = 2.0
+    for ox, oy, oz in itertools.product(OFFSETS, repeat=3):
+        offset = np.array([ox, oy, oz])
+        for sign in (1.0, -1.0):
+            for axis in range(3):
+                d = np.zeros(3)
+                d[axis] = sign
+                expected = np.zeros(3)
+                expected[axis] = radius * sign
+                hit, loc, nrm, _, _ = shape_intersect(orc, SPHERE, list(offset) + [radius], np.zeros(3) + offset, d)
+                assert hit == 1
+                assert np.array_equal(loc, expected + offset)
+                assert np.array_equal(nrm, d)
+
+
+def test_sphere_bounds(orc):  # test_shape.rs:98-109
+    out = np.zeros(6)
+    orc.orc_shape_bounds(SPHERE, P(0, 0, 0, 1), out.ctypes.data)
+    assert np.array_equal(out, [-1, -1, -1, 1, 1, 1])
+    orc.orc_shape_bounds(SPHERE, P(-2, 3, 0, 1), out.ctypes.data)
+    assert np.array_equal(out, [-3, 2, -1, -1, 4, 1])
+
+
+TRI = [1, 0, 0, 1, 1, 0, 2, 0, 0]  # test_shape.rs:126-128
+
+
+def test_triangle_bounds(orc):  # :131-133
+    out = np.zeros(6)
+    orc.orc_shape_bounds(TRIANGLE, P(*TRI), out.ctypes.data)
+    assert np.array_equal(out, [1, 0, 0, 2, 1, 0])
+
+
+def test_triangle_intersect_vertices(orc):  # :136-151
+    for point in ([1, 0, 0], [1, 1, 0], [2, 0, 0]):
+        hit, _, nrm, _, tmax = shape_intersect(orc, TRIANGLE, TRI, [point[0], point[1], -2.0], [0, 0, 1])
+        assert hit == 1 and tmax == 2.0
+        assert np.array_equal(nrm, [0, 0, 1])
+
+
+def test_triangle_from_behind(orc):  # :153-161 -- the normal is not face-forwarded
+    hit, _, nrm, _, tmax = shape_intersect(orc, TRIANGLE, TRI, [1, 0, 2], [0, 0, -1])
+    assert hit == 1 and tmax == 2.0
+    assert np.array_equal(nrm, [0, 0, 1])
+
+
+def test_triangle_parallel(orc):  # :163-168
+    d = np.array([1.0, 1.0, 0.0]) / np.sqrt(2.0)
+    hit, *_ = shape_intersect(orc, TRIANGLE, TRI, [0, 0, 0], d)
+    assert hit == 0
+
+
+def test_triangle_random_points(orc):  # :170-199 (the reference draws one thread_rng point; 500 seeded ones here)
+    rng = np.random.default_rng(7)
+    v0, e1, e2 = np.array([1.0, 0, 0]), np.array([0.0, 1, 0]), np.array([1.0, 0, 0])
+    for _ in range(500):
+        u, v = rng.uniform(0, 1, 2)
+        target = v0 + e1 * u + e2 * v
+        origin = np.array([0.0, 0, -2])
+        d = target - origin
+        dist = np.linalg.norm(d)
+        hit, _, nrm, _, tmax = shape_intersect(orc, TRIANGLE, TRI, origin, d / dist)
+        if u + v <= 1.0 - 1e-12:
+            assert hit == 1 and abs(tmax - dist) <= EPS
+            assert np.array_equal(nrm, [0, 0, 1])
+        elif u + v >= 1.0 + 1e-12:
+            assert hit == 0
+
+
+# ---- tests/test_bvh.rs ----------------------------------------------------------------------------------------------
+
+def _two_sphere_scene():
+    import craytracer_b200 as c
+    text = """{ camera: Perspective { origin: Point(0,0,-5), target: Point(0,0,0), up: Vector(0,1,0), fov: 60, film: { width: 8, height: 8 } },
+      lights: [ Infinite { intensity: Color(1,1,1) } ],
+      materials: { m: Matte { reflectance: Color(1,1,1), sigma: 0 } },
+      shapes: { a: Sphere { origin: Point(0.5,0.5,0.5), radius: 0.5 }, b: Sphere { origin: Point(1.5,0.5,0.5), radius: 0.5 } },
+      primitives: [ Shape { shape: 'a', material: 'm' }, Shape { shape: 'b', material: 'm' } ] }"""
+    return c.parse_scene(text)
+
+
+@pytest.mark.parametrize("sah", [False, True])
+def test_bvh_node(sah):  # test_bvh.rs:16-66 (SplitMethod::Median there; SAH is what Scene::new uses)
+    hs = _two_sphere_scene()
+    scene = o.OracleScene(hs, sah=sah)
+    cases = [([-1, 0.5, 0.5], [1, 0, 0], [0, 0.5, 0.5]), ([3, 0.5, 0.5], [-1, 0, 0], [2, 0.5, 0.5]),
+             ([0.5, 0.5, 0.5], [1, 0, 0], [1, 0.5, 0.5]), ([0.5, 0.5, 0.5], [-1, 0, 0], [0, 0.5, 0.5])]
+    import craytracer_b200 as c
+    rays = c.make_rays([k[0] for k in cases], [k[1] for k in cases])
+    hits, surf = scene.intersect(rays, surface=True)
+    assert (hits["prim"] != c.CRAY_NO_HIT).all()
+    for i, k in enumerate(cases):
+        assert np.array_equal(surf["location"][i], k[2])
+
+
+# ---- tests/test_bounds.rs ---------------------------------------------------------------------------------------------
+
+def bounds_hit(orc, mn, mx, origin, direction):
+    r = o.ray(origin, direction)
+    return orc.orc_bounds_intersects(P(*mn), P(*mx), r.ctypes.data) == 1
+
+
+def test_bounds_intersect_axes(orc):  # :9-27
+    for d in ([1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]):
+        assert bounds_hit(orc, [-1, -1, -1], [1, 1, 1], [0, 0, 0], d)
+
+
+def test_bounds_intersect_random(orc):  # :29-49
+    rng = np.random.default_rng(3)
+    for _ in range(100):
+        target = np.array([-1.0, rng.uniform(-1, 1), rng.uniform(-1, 1)])
+        d = target - np.array([-2.0, 0, 0])
+        assert bounds_hit(orc, [-1, -1, -1], [1, 1, 1], [-2, 0, 0], d / np.linalg.norm(d))
+
+
+def test_bounds_intersect_miss(orc):  # :51-63
+    assert not bounds_hit(orc, [0, 0, 0], [1, 1, 1], [0, 2, 0], [1, 0, 0])
+    assert not bounds_hit(orc, [0, 0, 0], [1, 1, 1], [0, -2, 0], [-1, 0, 0])
+    assert not bounds_hit(orc, [0, 0, 0], [1, 1, 1], [2, 0, 0], [0, 1, 0])
+    assert not bounds_hit(orc, [0, 0, 0], [1, 1, 1], [-2, 0, 0], [0, -1, 0])
+
+
+def test_bounds_sum(orc):  # :65-108
+    out = np.zeros(6)
+    for a, b, want in (([0, 0, 0, 1, 0, 0], [0, 0, 0, 1, 0, 0], [0, 0, 0, 1, 0, 0]), ([0, 0, 0, 1, 0, 0], [0, 0, 0, 0, 1, 0], [0, 0, 0, 1, 1, 0]),
+                       ([0, 0, 0, 1, 1, 1], [2, 2, 2, 3, 3, 3], [0, 0, 0, 3, 3, 3])):
+        orc.orc_bounds_union(P(*a), P(*b), out.ctypes.data)
+        assert np.array_equal(out, want)
+
+
+# ---- tests/test_bxdf.rs -------------------------------------------------------------------------------------------------
+
+def test_reflect(orc):  # :9-15
+    d = np.array([-1.0, 1, 0]) / np.sqrt(2.0)
+    out = np.zeros(3)
+    orc.orc_reflect(d.ctypes.data, P(0, 1, 0), out.ctypes.data)
+    assert np.abs(out - np.array([1.0, 1, 0]) / np.sqrt(2.0)).max() <= EPS
+
+
+def test_refract(orc):  # :17-25
+    d = np.array([-1.0, 1, 0]) / np.sqrt(2.0)
+    out = np.zeros(3)
+    assert orc.orc_refract(d.ctypes.data, P(0, 1, 0), float(d[1]), 1.0, 1.0, out.ctypes.data) == 1
+    assert np.abs(out - np.array([1.0, -1, 0]) / np.sqrt(2.0)).max() <= EPS
+
+
+# ---- tests/test_transformation.rs ---------------------------------------------------------------------------------------
+
+def xform(orc, kind, *params):
+    m, inv = np.zeros(16), np.zeros(16)
+    orc.orc_transformation(kind, P(*params), m.ctypes.data, inv.ctypes.data)
+    return m, inv
+
+
+def apply(orc, t, what, v):
+    out = np.zeros(3)
+    orc.orc_transform_apply(t[0].ctypes.data, t[1].ctypes.data, what, P(*v), out.ctypes.data)
+    return out
+
+
+POINT, VECTOR, NORMAL = 0, 1, 2
+
+
+def test_matrix_mul(orc):  # :7-37
+    m1 = o.f64(16, 3, 2, 13, 5, 10, 11, 8, 9, 6, 7, 12, 4, 15, 14, 1)
+    m2 = o.f64(1, 14, 14, 4, 11, 7, 6, 9, 8, 10, 10, 5, 13, 2, 3, 15)
+    m3 = o.f64(234, 291, 301, 296, 307, 266, 264, 285, 287, 262, 268, 305, 294, 303, 289, 236)
+    out = np.zeros(16)
+    orc.orc_matrix_mul(m1.ctypes.data, m2.ctypes.data, out.ctypes.data)
+    assert np.array_equal(out, m3)
+    eye = np.eye(4).ravel()
+    for m in (m1, m2):
+        orc.orc_matrix_mul(m.ctypes.data, eye.ctypes.data, out.ctypes.data)
+        assert np.array_equal(out, m)
+        orc.orc_matrix_mul(eye.ctypes.data, m.ctypes.data, out.ctypes.data)
+        assert np.array_equal(out, m)
+
+
+def test_matrix_inverse(orc):  # :39-69
+    m = o.f64(1, 3, 5, 4, 1, 3, 1, 2, 0, 3, 4, 3, 0, 2, 0, 1)
+    inv = np.zeros(16)
+    assert orc.orc_matrix_inverse(m.ctypes.data, inv.ctypes.data) == 1
+    want = o.f64(-1 / 4, 5 / 4, 0, -3 / 2, -1, 1, 1, -1, -3 / 4, 3 / 4, 1, -3 / 2, 2, -2, -2, 3)
+    assert np.abs(inv - want).max() <= EPS
+    prod = np.zeros(16)
+    orc.orc_matrix_mul(m.ctypes.data, inv.ctypes.data, prod.ctypes.data)
+    assert np.array_equal(prod, np.eye(4).ravel())
+    sing = o.f64(1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0)
+    assert orc.orc_matrix_inverse(sing.ctypes.data, inv.ctypes.data) == 0
+
+
+def test_translation(orc):  # :83-99
+    t = xform(orc, 0, 5.0, -3.0, 2.0)
+    assert np.array_equal(apply(orc, t, POINT, [-3, 4, 5]), [2, 1, 7])
+    assert np.array_equal(apply(orc, t, VECTOR, [-3, 4, 5]), [-3, 4, 5])
+    assert np.array_equal(apply(orc, t, NORMAL, [-3, 4, 5]), [-3, 4, 5])
+    out = np.zeros(6)
+    orc.orc_transform_bounds(t[0].ctypes.data, t[1].ctypes.data, P(0, 0, 0, 1, 2, 3), out.ctypes.data)
+    assert np.array_equal(out, [5, -3, 2, 6, -1, 5])
+
+
+def test_scale(orc):  # :101-120
+    t = xform(orc, 1, 2.0, -3.0, 0.5)
+    assert np.array_equal(apply(orc, t, POINT, [-3, 4, 5]), [-6, -12, 2.5])
+    assert np.array_equal(apply(orc, t, VECTOR, [-3, 4, 5]), [-6, -12, 2.5])
+    assert np.array_equal(apply(orc, t, NORMAL, [-3, 4, 5]), [-3.0 / 2.0, -4.0 / 3.0, 5.0 / 0.5])
+    out = np.zeros(6)
+    orc.orc_transform_bounds(t[0].ctypes.data, t[1].ctypes.data, P(0, 0, 0, 1, 2, 3), out.ctypes.data)
+    assert np.array_equal(out, [0, -6, 0, 2, 0, 1.5])
+
+
+@pytest.mark.parametrize("kind,want", [(2, [2, -3, 1]), (3, [3, 1, -2]), (4, [-1, 2, 3])])
+def test_rotations(orc, kind, want):  # :122-162
+    t = xform(orc, kind, np.deg2rad(90.0))
+    for what in (POINT, VECTOR, NORMAL):
+        assert np.abs(apply(orc, t, what, [2, 1, 3]) - want).max() <= EPS
+
+
+def test_look_at(orc):  # :164-173
+    t = xform(orc, 5, 9, 0, 0, 10, 0, 0, 0, 0, 1)
+    assert np.abs(apply(orc, t, POINT, [0, 0, 0]) - [9, 0, 0]).max() <= EPS
+    assert np.abs(apply(orc, t, VECTOR, [0, 0, 1]) - [1, 0, 0]).max() <= EPS
+    assert np.abs(apply(orc, t, VECTOR, [0, 1, 0]) - [0, 0, 1]).max() <= EPS
+    assert np.abs(apply(orc, t, VECTOR, [1, 0, 0]) - [0, 1, 0]).max() <= EPS
+
+
+def test_perspective(orc):  # :175-186
+    t = xform(orc, 6, 90.0, 50.0, 100.0)
+    assert np.abs(apply(orc, t, POINT, [0, 0, 50]) - [0, 0, 0]).max() <= EPS
+    assert np.abs(apply(orc, t, POINT, [0, 0, 100]) - [0, 0, 1]).max() <= EPS
+    assert np.abs(apply(orc, t, POINT, [0, 0, 75]) - [0, 0, (100.0 / 50.0) / (75.0 / 25.0)]).max() <= EPS
+
+
+# ---- tests/test_color.rs, tests/test_util.rs ---------------------------------------------------------------------------
+
+def test_color_from_to_rgb(orc):  # test_color.rs:4-20
+    out = np.zeros(3)
+    orc.orc_from_rgb(255, 128, 0, out.ctypes.data)
+    assert np.abs(out - [1.0, (128 / 255.0) ** 2.2, 0.0]).max() <= EPS
+    back = np.zeros(3, dtype=np.uint8)
+    orc.orc_to_rgb(out.ctypes.data, back.ctypes.data)
+    assert list(back) in ([255, 128, 0], [255, 127, 0])  # `as u8` truncates: 127.99999 -> 127 is the reference's own behaviour
+    for rgb in ((0, 0, 0), (255, 255, 255), (12, 200, 77)):
+        orc.orc_from_rgb(*rgb, out.ctypes.data)
+        orc.orc_to_rgb(out.ctypes.data, back.ctypes.data)
+        assert np.abs(back.astype(int) - rgb).max() <= 1
+
+
+@pytest.mark.parametrize("data,kind,k", [([], 0, 0), ([1], 1, 0), ([1], 1, 1), ([1, 2, 3], 0, 0), ([1, 2, 3], 0, 1), ([1, 2, 3], 0, 2), ([1, 2, 3], 0, 3),
+                                         ([1, 2, 3, 4, 5], 2, 0), ([1, 2, 3, 4, 5], 2, 1)])
+def test_partition_by(orc, data, kind, k):  # test_util.rs
+    arr = np.array(data, dtype=np.uint32)
+    pred = (lambda v: v > k) if kind == 0 else ((lambda v: v == k) if kind == 1 else (lambda v: v % 2 == k))
+    mid = orc.orc_partition_by(arr.ctypes.data if len(arr) else None, len(arr), kind, k)
+    assert sorted(arr.tolist()) == sorted(data)
+    assert all(pred(v) for v in arr[:mid]) and not any(pred(v) for v in arr[mid:])
+
+
+# ---- sampler pins (third-party arithmetic, see oracle/sampling.hpp) -------------------------------------------------------
+
+def test_siphash24_reference_vector(orc):
+    # Aumasson & Bernstein, SipHash paper Appendix A: key 00..0f, message 00..0e
+    msg = bytes(range(15))
+    k0 = int.from_bytes(bytes(range(8)), "little")
+    k1 = int.from_bytes(bytes(range(8, 16)), "little")
+    assert orc.orc_siphash(2, 4, k0, k1, msg, len(msg)) == 0xA129CA6149BE45E5
+
+
+def test_siphash13_zero_key_matches_cpython(orc):
+    # CPython >= 3.11 hashes bytes with SipHash-1-3; PYTHONHASHSEED=0 zeroes the key, which is exactly Rust's
+    # DefaultHasher::new() (SipHasher13 with keys 0, 0).
+    msgs = [b"a", b"abcdefgh", bytes(range(24)), (7).to_bytes(8, "little") + (600).to_bytes(8, "little") + (399).to_bytes(8, "little")]
+    code = "import sys\nassert sys.hash_info.algorithm == 'siphash13', sys.hash_info.algorithm\n" + "\n".join(f"print(hash({m!r}) & (2**64-1))" for m in msgs)
+    env = dict(os.environ, PYTHONHASHSEED="0")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    if res.returncode != 0:
+        pytest.skip("interpreter does not hash with siphash13: " + res.stderr.strip()[-80:])
+    want = [int(x) for x in res.stdout.split()]
+    for m, w in zip(msgs, want):
+        got = orc.orc_siphash(1, 3, 0, 0, m, len(m))
+        if got == 0xFFFFFFFFFFFFFFFF:  # CPython maps -1 to -2
+            continue
+        assert got == w, m
+    assert orc.orc_pixel_hash(7, 600, 399) == want[-1] & 0xFFFFFFFF
+
+
+def test_sobol_is_a_scrambled_01_sequence(orc):
+    # Owen scrambling keeps the (0, m, 1)-net property: every aligned block of 2^k indices hits each of the 2^k strata once
+    for dim in (0, 1, 5, 17, 67):
+        for seed in (0, 12345, 0xDEADBEEF):
+            vals = np.array([orc.orc_sobol_sample(i, dim, seed) for i in range(256)])
+            assert (vals >= 0).all() and (vals < 1).all()
+            for k in (4, 6, 8):
+                n = 1 << k
+                for block in range(0, 256, n):
+                    strata = np.floor(vals[block:block + n] * n).astype(int)
+                    assert sorted(strata) == list(range(n)), (dim, seed, k, block)
+    # different seeds / dimensions decorrelate
+    a = np.array([orc.orc_sobol_sample(i, 0, 1) for i in range(1024)])
+    b = np.array([orc.orc_sobol_sample(i, 1, 1) for i in range(1024)])
+    assert abs(np.corrcoef(a, b)[0, 1]) < 0.1
+    assert abs(a.mean() - 0.5) < 0.01 and abs(b.mean() - 0.5) < 0.01

@@ -13,7 +13,7 @@ def rand_rays(bounds_lo, bounds_hi, n, seed=1):
     d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
     return c.make_rays(org, d)
 
-def compare(name, hs, lo, hi, n_rand=200000, spp_check=2):
+def compare(name, hs, lo, hi, n_rand=200000, spp_check=2, perf_spp=0):
     t = time.time(); sc = c.Scene(hs); t_create = time.time() - t
     orc = o.OracleScene(hs)
     W, H = sc.width, sc.height
@@ -56,6 +56,11 @@ def compare(name, hs, lo, hi, n_rand=200000, spp_check=2):
     print(f"  oracle render: {dt:.2f}s rays={int(counts[0]+counts[1])} ({(counts[0]+counts[1])/dt/1e6:.2f} Mrays/s) mean={ofilm.mean()/spp_check:.5f} nan={counts[2]}")
     film, st = sc.render(sample_begin=0, sample_end=spp_check, mode=c.TRAVERSE_EXACT)
     d = np.abs(film - ofilm); print(f"  film exact vs oracle: max abs diff {d.max():.3e}, rel-mse {np.mean((film-ofilm)**2/(ofilm**2+1e-2)):.3e}; counts gpu=({st.closest_rays},{st.shadow_rays}) oracle=({counts[0]},{counts[1]})")
+    if perf_spp:
+        for rep in range(2):
+            film, st = sc.render(sample_begin=0, sample_end=perf_spp, mode=c.TRAVERSE_FAST)
+            rays = st.closest_rays + st.shadow_rays
+            print(f"  PERF fast spp={perf_spp}: {st.render_ms:.1f} ms, trace(extend) {st.trace_ms:.1f} ms, rays={rays} -> {rays/st.render_ms/1e3:.1f} Mrays/s, {st.samples/st.render_ms/1e3:.2f} Msamples/s, iters={st.iterations}, closest={st.closest_rays} ({st.closest_rays/st.trace_ms/1e3:.1f} M closest rays/s in k_extend)")
     sc.close(); orc.close()
 
 if __name__ == "__main__":
@@ -68,7 +73,7 @@ if __name__ == "__main__":
         elif name == "dragon":
             scenes.register_standins()
             t = time.time(); hs = c.parse_scene(scenes.dragon(), base_dir="/nonexistent"); print("parse+standin", time.time() - t)
-            compare(name, hs, [-120, -45, -60], [120, 60, 60], n_rand=1000000)
+            compare(name, hs, [-120, -45, -60], [120, 60, 60], n_rand=1000000, spp_check=1, perf_spp=32)
         else:
             hs = c.parse_scene(scenes.CONFIGS[name](width=200, height=120))
             compare(name, hs, [-10, -2, -10], [10, 10, 20])
