@@ -22,16 +22,30 @@ __device__ __forceinline__ LeafPrim load_leaf_prim(const LeafPrim* p) {
 
 // Shape::Triangle arm of intersect / intersects (shape.rs:214-262, :345-367) up to, but not including, the
 // final range check: true iff the determinant / u / v tests pass; t is the hit distance.
+//
+// The reference divides three times (u, v, t).  Most candidates fail the u or v test, so the quotients are only
+// formed when the cheap tests on the numerators cannot decide; the guards below are chosen so that they can never
+// disagree with the reference's comparisons on the rounded quotients:
+//   * opposite signs of numerator and denominator  =>  quotient < 0 (the 1e-290 floor keeps clear of underflow to -0)
+//   * |numerator| > |denominator| * (1 + 2^-40)     =>  the rounded quotient is > 1
+// When the tests pass, u, v and t are exactly the reference's values.
 __device__ __forceinline__ bool triangle_eval(const double* d9, V3 o, V3 dir, double& t, double& u, double& v) {
     const V3 v0 = mk(d9[0], d9[1], d9[2]), e1 = mk(d9[3], d9[4], d9[5]), e2 = mk(d9[6], d9[7], d9[8]);
     const V3 P = cross(dir, e2);
     const double denominator = dot(P, e1);
     if (denominator > -kEpsilon && denominator < kEpsilon) return false;
     const V3 T = o - v0;
-    u = dot(P, T) / denominator;
-    if (u < 0.0 || u > 1.0) return false;
+    const double un = dot(P, T);
+    const double ad = fabs(denominator), slack = ad * 1.0000000000009095;  // 1 + 2^-40
+    if (fabs(un) > 1e-290 && (un < 0.0) != (denominator < 0.0)) return false;  // u < 0
+    if (fabs(un) > slack) return false;                                       // u > 1
     const V3 Q = cross(T, e1);
-    v = dot(Q, dir) / denominator;
+    const double vn = dot(Q, dir);
+    if (fabs(vn) > 1e-290 && (vn < 0.0) != (denominator < 0.0)) return false;  // v < 0
+    if (fabs(vn) > slack) return false;                                       // v > 1 and u >= 0  =>  u + v > 1
+    u = un / denominator;
+    if (u < 0.0 || u > 1.0) return false;
+    v = vn / denominator;
     if (v < 0.0 || u + v > 1.0) return false;
     t = dot(Q, e2) / denominator;  // T.cross(e1).dot(e2): the same value as Q, recomputed in the reference
     return true;

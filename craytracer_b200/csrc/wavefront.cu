@@ -6,11 +6,17 @@
 //
 // Wavefront pipeline (replaces render / render_tile / render_pixel / estimate_Li, src/bin/craytracer.rs:148-291 and
 // src/path_integrator.rs:41-215): a pool of path slots lives in HBM as structure-of-arrays; every iteration runs
-//   k_generate  flush finished paths into the film, refill their slots with new camera rays (sampler + camera)
-//   k_extend    closest-hit traversal of every live path's ray
-//   k_shade     one path vertex: emission, light sample + shadow ray, BSDF sample, Russian roulette
-//   k_shadow    any-hit traversal of the shadow rays, adds the unoccluded light contributions
+//   k_generate  flush finished paths into the film, refill their slots with new camera rays (sampler + camera),
+//               append every live slot to the extend queue
+//   extend      closest-hit traversal of the queued rays (k_wide_persistent<false> / k_extend_exact)
+//   k_shade     one path vertex: emission, light sample + shadow ray, BSDF sample, Russian roulette; appends the
+//               slots whose light sample can contribute to the shadow queue
+//   shadow      any-hit traversal of the queued shadow rays, adds the unoccluded contributions
 // so all lanes keep working until the sample range is exhausted (path regeneration).
+//
+// Fast-mode traversal runs as a persistent kernel: every warp pulls rays from the queue with one atomic per refill,
+// steps its 32 traversals in lock-step (node phase, then primitive phase -- see WideTraversal) and refills idle lanes
+// once enough of them have finished, so SIMD lanes are not parked behind the longest ray of a fixed assignment.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -34,6 +40,7 @@ struct Pool {  // structure-of-arrays over `capacity` path slots
     double *sdx, *sdy, *sdz, *smax, *sc_r, *sc_g, *sc_b;  // pending shadow ray (origin = ox,oy,oz) and its contribution
     uint32_t *id, *pixel, *hash, *shuffled_rev;    // job-relative sample id, film offset, sampler state
     uint32_t* state;                               // state | bounces << 8 | specular << 16 | shadow_pending << 17 | bad << 18
+    uint32_t *extend_queue, *shadow_queue;         // slot indices with a ray to extend / a shadow ray to test this iteration
 };
 
 struct Job {
@@ -51,67 +58,169 @@ struct Job {
 
 struct Counters {
     unsigned long long next_id;
-    unsigned long long live;         // ACTIVE slots after the last k_generate
     unsigned long long closest_rays, shadow_rays, nan_samples;
+    // per-iteration part, cleared before every k_generate
+    unsigned long long n_extend, n_shadow;          // queue lengths
+    unsigned long long extend_cursor, shadow_cursor;  // persistent-kernel fetch positions
 };
 
 __device__ __forceinline__ uint32_t st_state(uint32_t s) { return s & 0xFFu; }
 __device__ __forceinline__ uint32_t st_bounces(uint32_t s) { return (s >> 8) & 0xFFu; }
 
-template <bool ANY>
-__device__ __forceinline__ bool trace(const SceneView& s, int exact, V3 o, V3 d, double ray_max, Hit& hit) {
-    if (exact) return traverse_exact<ANY>(s, o, d, ray_max, hit);
-    return traverse_wide<ANY>(s, o, d, ray_max, hit);
-}
+// ---- ray sources for the persistent wide-BVH kernel -------------------------------------------------------------
 
-// ---- S3 kernels ---------------------------------------------------------------------------------------------
+struct ExtendSource {  // queued path rays -> Pool::hit_*
+    Pool p;
+    __device__ __forceinline__ uint32_t load(uint64_t idx, V3& o, V3& d, double& ray_max) const {
+        const uint32_t i = p.extend_queue[idx];
+        o = mk(p.ox[i], p.oy[i], p.oz[i]);
+        d = mk(p.dx[i], p.dy[i], p.dz[i]);
+        ray_max = inf_f64();
+        return i;
+    }
+    __device__ __forceinline__ void store(const SceneView&, uint32_t i, const WideTraversal<false>& t) const {
+        p.hit_slot[i] = t.hit.slot;
+        p.hit_t[i] = t.hit.t; p.hit_u[i] = t.hit.u; p.hit_v[i] = t.hit.v;
+    }
+};
 
-__global__ void __launch_bounds__(128) k_trace_closest(SceneView s, int exact, const cray_ray* __restrict__ rays, uint64_t n, cray_hit* __restrict__ hits,
-                                                        cray_surface* __restrict__ surf) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const cray_ray r = rays[i];
-    const V3 o = mk(r.origin[0], r.origin[1], r.origin[2]), d = mk(r.direction[0], r.direction[1], r.direction[2]);
-    Hit h;
+struct ShadowSource {  // queued shadow rays -> L += contribution when unoccluded (path_integrator.rs:141-163)
+    Pool p;
+    __device__ __forceinline__ uint32_t load(uint64_t idx, V3& o, V3& d, double& ray_max) const {
+        const uint32_t i = p.shadow_queue[idx];
+        o = mk(p.ox[i], p.oy[i], p.oz[i]);
+        d = mk(p.sdx[i], p.sdy[i], p.sdz[i]);
+        ray_max = p.smax[i];
+        return i;
+    }
+    __device__ __forceinline__ void store(const SceneView&, uint32_t i, bool occluded) const {
+        if (!occluded) { p.L_r[i] += p.sc_r[i]; p.L_g[i] += p.sc_g[i]; p.L_b[i] += p.sc_b[i]; }
+    }
+};
+
+__device__ __forceinline__ void write_hit(const SceneView& s, const LeafPrim* prims, const cray_ray& r, const Hit& h, bool found, uint64_t i,
+                                          cray_hit* hits, cray_surface* surf) {
     cray_hit out;
     out._pad = 0;
-    if (trace<false>(s, exact, o, d, r.max_distance, h)) {
-        const LeafPrim lp = load_leaf_prim((exact ? s.bin_prims : s.wide_prims) + h.slot);
+    cray_surface sf;
+    memset(&sf, 0, sizeof(sf));
+    if (found) {
+        const V3 o = mk(r.origin[0], r.origin[1], r.origin[2]), d = mk(r.direction[0], r.direction[1], r.direction[2]);
+        const LeafPrim lp = load_leaf_prim(prims + h.slot);
         V3 loc, nrm;
         double tu, tv;
-        // spheres / disks accept in object space and may report ray.max_distance instead of t (primitive.rs:65);
-        // their surface point is always at the accepted root, which equals h.t whenever max_distance > EPSILON
         surface_at(s, lp, o, d, h.t, h.u, h.v, loc, nrm, tu, tv);
         const bool tri = (lp.kind & 0xFFu) == PRIM_TRIANGLE;
         out.prim = lp.prim;
         out.t = h.t;
-        out.u = tri ? h.u : tu;
+        out.u = tri ? h.u : tu;  // triangles: Moeller-Trumbore barycentrics; spheres / disks: surface uv
         out.v = tri ? h.v : tv;
-        if (surf) {
-            cray_surface sf;
-            sf.location[0] = loc.x; sf.location[1] = loc.y; sf.location[2] = loc.z;
-            sf.normal[0] = nrm.x; sf.normal[1] = nrm.y; sf.normal[2] = nrm.z;
-            sf.uv[0] = tu; sf.uv[1] = tv;
-            surf[i] = sf;
-        }
+        sf.location[0] = loc.x; sf.location[1] = loc.y; sf.location[2] = loc.z;
+        sf.normal[0] = nrm.x; sf.normal[1] = nrm.y; sf.normal[2] = nrm.z;
+        sf.uv[0] = tu; sf.uv[1] = tv;
     } else {
         out.prim = CRAY_NO_HIT;
         out.t = 0.0; out.u = 0.0; out.v = 0.0;
-        if (surf) {
-            cray_surface sf;
-            memset(&sf, 0, sizeof(sf));
-            surf[i] = sf;
-        }
     }
     hits[i] = out;
+    if (surf) surf[i] = sf;
 }
 
-__global__ void __launch_bounds__(128) k_trace_any(SceneView s, int exact, const cray_ray* __restrict__ rays, uint64_t n, uint8_t* __restrict__ occluded) {
+struct RayArraySource {  // S3: caller-provided cray_ray records
+    const cray_ray* rays;
+    cray_hit* hits;
+    cray_surface* surf;
+    uint8_t* occluded;
+    __device__ __forceinline__ uint32_t load(uint64_t idx, V3& o, V3& d, double& ray_max) const {
+        const cray_ray r = rays[idx];
+        o = mk(r.origin[0], r.origin[1], r.origin[2]);
+        d = mk(r.direction[0], r.direction[1], r.direction[2]);
+        ray_max = r.max_distance;
+        return (uint32_t)idx;
+    }
+    __device__ __forceinline__ void store(const SceneView& s, uint32_t i, const WideTraversal<false>& t) const {
+        write_hit(s, s.wide_prims, rays[i], t.hit, t.hit.slot != CRAY_NO_HIT, i, hits, surf);
+    }
+    __device__ __forceinline__ void store(const SceneView&, uint32_t i, bool occ) const { occluded[i] = occ ? 1 : 0; }
+};
+
+// ---- persistent wide-BVH traversal ----------------------------------------------------------------------------------
+//
+// One warp = 32 concurrent traversals stepped in lock-step.  Per loop iteration:
+//   refill  if at least kRefillLanes lanes are idle (or all are), one atomicAdd claims that many queue entries
+//   node    lanes with a pending interior child visit it (8 quantised box tests, f32)
+//   prim    lanes with queued leaf primitives test ONE of them in f64 -- but only when at least kPrimLanes lanes have
+//           such work or some lane has nothing else left to do, so the f64 phase runs with many lanes at once
+//   advance pop stacks; finished lanes write their result and become idle
+constexpr int kRefillLanes = 8;
+constexpr int kPrimLanes = 10;
+
+template <bool ANY, class Source>
+__global__ void __launch_bounds__(128) k_wide_persistent(SceneView s, Source src, const unsigned long long* __restrict__ n_ptr, unsigned long long* cursor) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long n = *n_ptr;
+    WideTraversal<ANY> t;
+    t.live = false;
+    uint32_t id = 0;
+    bool exhausted = false;
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, !t.live);
+        if (!exhausted && (idle == FULL || __popc(idle) >= kRefillLanes)) {
+            const int want = __popc(idle);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(cursor, (unsigned long long)want);
+            base = __shfl_sync(FULL, base, 0);
+            if (!t.live) {
+                const unsigned long long idx = base + __popc(idle & ((1u << lane) - 1u));
+                if (idx < n) {
+                    V3 o, d;
+                    double ray_max;
+                    id = src.load(idx, o, d, ray_max);
+                    t.begin(o, d, ray_max);
+                }
+            }
+            if (base + want >= n) exhausted = true;
+        }
+        if (__ballot_sync(FULL, t.live) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        if (t.live && t.has_node_work()) t.node_step(s);
+        const bool wants_prim = t.live && t.has_prim_work();
+        const unsigned prim_lanes = __ballot_sync(FULL, wants_prim);
+        const unsigned starved = __ballot_sync(FULL, wants_prim && !t.has_node_work());
+        bool finished = false;
+        if (wants_prim && (starved != 0u || __popc(prim_lanes) >= kPrimLanes)) finished = t.prim_step(s);
+        if (t.live) {
+            if constexpr (ANY) {
+                if (finished) { src.store(s, id, true); t.live = false; }
+                else if (t.advance()) { src.store(s, id, false); t.live = false; }
+            } else {
+                if (t.advance()) { src.store(s, id, t); t.live = false; }
+            }
+        }
+    }
+}
+
+// ---- exact-mode kernels (reference binary BVH, one thread per ray) ------------------------------------------------------
+
+__global__ void __launch_bounds__(128) k_trace_closest_exact(SceneView s, const cray_ray* __restrict__ rays, uint64_t n, cray_hit* __restrict__ hits,
+                                                              cray_surface* __restrict__ surf) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const cray_ray r = rays[i];
     Hit h;
-    occluded[i] = trace<true>(s, exact, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), r.max_distance, h) ? 1 : 0;
+    const bool found = traverse_exact<false>(s, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), r.max_distance, h);
+    write_hit(s, s.bin_prims, r, h, found, i, hits, surf);
+}
+
+__global__ void __launch_bounds__(128) k_trace_any_exact(SceneView s, const cray_ray* __restrict__ rays, uint64_t n, uint8_t* __restrict__ occluded) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const cray_ray r = rays[i];
+    Hit h;
+    occluded[i] = traverse_exact<true>(s, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), r.max_distance, h) ? 1 : 0;
 }
 
 // ---- wavefront kernels --------------------------------------------------------------------------------------
@@ -119,6 +228,16 @@ __global__ void __launch_bounds__(128) k_trace_any(SceneView s, int exact, const
 __device__ __forceinline__ void warp_count(unsigned long long* counter, bool pred) {
     const unsigned mask = __ballot_sync(__activemask(), pred);
     if (pred && (threadIdx.x & 31) == (unsigned)(__ffs(mask) - 1)) atomicAdd(counter, (unsigned long long)__popc(mask));
+}
+
+// Warp-aggregated append of `value` to a device queue (one atomic per converged group of lanes).
+__device__ __forceinline__ void queue_append(unsigned long long* counter, uint32_t* queue, uint32_t value) {
+    const unsigned m = __activemask();
+    const unsigned lane = threadIdx.x & 31u, leader = __ffs(m) - 1u;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    queue[base + __popc(m & ((1u << lane) - 1u))] = value;
 }
 
 // Camera::sample + generate_ray camera.rs:131-162
@@ -198,27 +317,26 @@ __global__ void __launch_bounds__(256) k_generate(SceneView s, Pool p, Job job, 
         }
     }
     p.state[i] = st;
-    warp_count(&counters->live, st_state(st) == SLOT_ACTIVE);
+    // every live slot has a ray to extend this iteration
+    if (st_state(st) == SLOT_ACTIVE) queue_append(&counters->n_extend, p.extend_queue, i);
 }
 
-__global__ void __launch_bounds__(128) k_extend(SceneView s, Pool p, Job job, Counters* counters) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.capacity) return;
-    const bool active = st_state(p.state[i]) == SLOT_ACTIVE;
-    warp_count(&counters->closest_rays, active);
-    if (!active) return;
+__global__ void __launch_bounds__(128) k_extend_exact(SceneView s, Pool p, const unsigned long long* __restrict__ n_ptr) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= *n_ptr) return;
+    const uint32_t i = p.extend_queue[q];
     Hit h;
-    trace<false>(s, job.exact, mk(p.ox[i], p.oy[i], p.oz[i]), mk(p.dx[i], p.dy[i], p.dz[i]), inf_f64(), h);
+    traverse_exact<false>(s, mk(p.ox[i], p.oy[i], p.oz[i]), mk(p.dx[i], p.dy[i], p.dz[i]), inf_f64(), h);
     p.hit_slot[i] = h.slot;
     p.hit_t[i] = h.t; p.hit_u[i] = h.u; p.hit_v[i] = h.v;
 }
 
 // One iteration of the `while` loop of estimate_Li (path_integrator.rs:54-212) for one path.
 __global__ void __launch_bounds__(128) k_shade(SceneView s, Pool p, Job job, Counters* counters) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.capacity) return;
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= counters->n_extend) return;
+    const uint32_t i = p.extend_queue[q];
     uint32_t st = p.state[i];
-    if (st_state(st) != SLOT_ACTIVE) return;
     const uint32_t bounces = st_bounces(st);
     const bool is_specular_bounce = (st >> 16) & 1u;
     bool bad = (st >> 18) & 1u;
@@ -306,11 +424,12 @@ __global__ void __launch_bounds__(128) k_shade(SceneView s, Pool p, Job job, Cou
         } else {
             contribution = beta * ls.Li * f * cos_theta / light_sampler_pdf;
         }
-        // the reference always casts the shadow ray (:141); it is counted as a ray here too, but only traced when
-        // an unoccluded result could change L
+        // the reference always casts the shadow ray (:141); it is counted as a ray here too, but only traced when an
+        // unoccluded result could change L
         warp_count(&counters->shadow_rays, true);
         if (!is_black(contribution) || !is_finite3(contribution)) {
             shadow_pending = true;
+            queue_append(&counters->n_shadow, p.shadow_queue, i);
             p.sdx[i] = ls.w_i.x; p.sdy[i] = ls.w_i.y; p.sdz[i] = ls.w_i.z;
             p.smax[i] = ls.shadow_max;
             p.sc_r[i] = contribution.r; p.sc_g[i] = contribution.g; p.sc_b[i] = contribution.b;
@@ -353,14 +472,12 @@ __global__ void __launch_bounds__(128) k_shade(SceneView s, Pool p, Job job, Cou
     }
 }
 
-__global__ void __launch_bounds__(128) k_shadow(SceneView s, Pool p, Job job) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.capacity) return;
-    const uint32_t st = p.state[i];
-    if (!((st >> 17) & 1u)) return;
-    p.state[i] = st & ~(1u << 17);
+__global__ void __launch_bounds__(128) k_shadow_exact(SceneView s, Pool p, const unsigned long long* __restrict__ n_ptr) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= *n_ptr) return;
+    const uint32_t i = p.shadow_queue[q];
     Hit h;
-    if (!trace<true>(s, job.exact, mk(p.ox[i], p.oy[i], p.oz[i]), mk(p.sdx[i], p.sdy[i], p.sdz[i]), p.smax[i], h)) {
+    if (!traverse_exact<true>(s, mk(p.ox[i], p.oy[i], p.oz[i]), mk(p.sdx[i], p.sdy[i], p.sdz[i]), p.smax[i], h)) {
         p.L_r[i] += p.sc_r[i]; p.L_g[i] += p.sc_g[i]; p.L_b[i] += p.sc_b[i];
     }
 }
@@ -379,15 +496,26 @@ struct PoolStorage {
     Counters* h_counters = nullptr;  // pinned
     double* d_film = nullptr;
     uint64_t film_elems = 0;
+    unsigned persistent_blocks = 0;   // SMs x resident CTAs of the persistent traversal kernel
+    unsigned long long* d_trace_counters = nullptr;  // {n, cursor} for the S3 entry points
 };
 
 int ensure_pool(cray_scene* sc, uint32_t capacity) {
     auto* ps = static_cast<PoolStorage*>(sc->pool);
     if (!ps) { ps = new PoolStorage(); sc->pool = ps; }
+    if (!ps->d_counters) {
+        CRAY_CUDA(cudaMalloc(&ps->d_counters, sizeof(Counters)));
+        CRAY_CUDA(cudaMallocHost(&ps->h_counters, sizeof(Counters)));
+        int sms = 0;
+        CRAY_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sc->device));
+        int per_sm = 0;
+        CRAY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wide_persistent<false, ExtendSource>, 128, 0));
+        ps->persistent_blocks = (unsigned)(sms * std::max(per_sm, 1));
+    }
     if (ps->pool.capacity >= capacity) return CRAY_OK;
     if (ps->slab) { cudaFree(ps->slab); ps->slab = nullptr; }
     const size_t n = capacity;
-    const size_t n_f64 = 24, n_u32 = 6;
+    const size_t n_f64 = 24, n_u32 = 8;
     const size_t bytes = n * (n_f64 * 8 + n_u32 * 4);
     CRAY_CUDA(cudaMalloc(&ps->slab, bytes));
     CRAY_CUDA(cudaMemsetAsync(ps->slab, 0, bytes, sc->stream));
@@ -398,14 +526,10 @@ int ensure_pool(cray_scene* sc, uint32_t capacity) {
     size_t k = 0;
     for (double** fp : fields) { *fp = f + k * n; ++k; }
     uint32_t* u = reinterpret_cast<uint32_t*>(f + n_f64 * n);
-    uint32_t** ufields[] = {&p.hit_slot, &p.id, &p.pixel, &p.hash, &p.shuffled_rev, &p.state};
+    uint32_t** ufields[] = {&p.hit_slot, &p.id, &p.pixel, &p.hash, &p.shuffled_rev, &p.state, &p.extend_queue, &p.shadow_queue};
     k = 0;
     for (uint32_t** up : ufields) { *up = u + k * n; ++k; }
     p.capacity = capacity;
-    if (!ps->d_counters) {
-        CRAY_CUDA(cudaMalloc(&ps->d_counters, sizeof(Counters)));
-        CRAY_CUDA(cudaMallocHost(&ps->h_counters, sizeof(Counters)));
-    }
     return CRAY_OK;
 }
 
@@ -416,28 +540,37 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
     auto* ps = static_cast<PoolStorage*>(sc->pool);
     Pool pool = ps->pool;
     pool.capacity = capacity;
+    Counters* dc = ps->d_counters;
     CRAY_CUDA(cudaMemsetAsync(pool.state, 0, sizeof(uint32_t) * capacity, stream));
-    CRAY_CUDA(cudaMemsetAsync(ps->d_counters, 0, sizeof(Counters), stream));
+    CRAY_CUDA(cudaMemsetAsync(dc, 0, sizeof(Counters), stream));
     cudaEvent_t e0, e1, t0, t1;
     CRAY_CUDA(cudaEventCreate(&e0)); CRAY_CUDA(cudaEventCreate(&e1));
     CRAY_CUDA(cudaEventCreate(&t0)); CRAY_CUDA(cudaEventCreate(&t1));
     CRAY_CUDA(cudaEventRecord(e0, stream));
-    const unsigned g256 = (capacity + 255) / 256, g128 = (capacity + 127) / 128;
-    uint64_t iterations = 0, launches = 0;
+    const unsigned g256 = (capacity + 255) / 256;
+    const unsigned gp = ps->persistent_blocks;
+    uint64_t iterations = 0, launches = 0, closest = 0;
     double trace_ms = 0.0;
+    const size_t per_iteration = sizeof(Counters) - offsetof(Counters, n_extend);
     for (;;) {
-        CRAY_CUDA(cudaMemsetAsync(&ps->d_counters->live, 0, sizeof(unsigned long long), stream));
-        k_generate<<<g256, 256, 0, stream>>>(sc->view, pool, job, ps->d_counters);
-        CRAY_CUDA(cudaMemcpyAsync(ps->h_counters, ps->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+        CRAY_CUDA(cudaMemsetAsync(&dc->n_extend, 0, per_iteration, stream));
+        k_generate<<<g256, 256, 0, stream>>>(sc->view, pool, job, dc);
+        CRAY_CUDA(cudaMemcpyAsync(ps->h_counters, dc, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
         CRAY_CUDA(cudaStreamSynchronize(stream));
         launches += 1;
-        if (ps->h_counters->live == 0) break;
+        const uint64_t live = ps->h_counters->n_extend;
+        if (live == 0) break;
+        closest += live;
+        const unsigned g_live = (unsigned)((live + 127) / 128);
         const bool timed = stats != nullptr;
         if (timed) CRAY_CUDA(cudaEventRecord(t0, stream));
-        k_extend<<<g128, 128, 0, stream>>>(sc->view, pool, job, ps->d_counters);
+        if (job.exact) k_extend_exact<<<g_live, 128, 0, stream>>>(sc->view, pool, &dc->n_extend);
+        else k_wide_persistent<false, ExtendSource><<<gp, 128, 0, stream>>>(sc->view, ExtendSource{pool}, &dc->n_extend, &dc->extend_cursor);
         if (timed) CRAY_CUDA(cudaEventRecord(t1, stream));
-        k_shade<<<g128, 128, 0, stream>>>(sc->view, pool, job, ps->d_counters);
-        k_shadow<<<g128, 128, 0, stream>>>(sc->view, pool, job);
+        k_shade<<<g_live, 128, 0, stream>>>(sc->view, pool, job, dc);
+        // at most one shadow ray per shaded vertex; the queue length lives on the device
+        if (job.exact) k_shadow_exact<<<g_live, 128, 0, stream>>>(sc->view, pool, &dc->n_shadow);
+        else k_wide_persistent<true, ShadowSource><<<gp, 128, 0, stream>>>(sc->view, ShadowSource{pool}, &dc->n_shadow, &dc->shadow_cursor);
         launches += 3;
         iterations += 1;
         if (timed) {
@@ -454,7 +587,7 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
     CRAY_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     if (stats) {
         stats->samples = job.n_total;
-        stats->closest_rays = ps->h_counters->closest_rays;
+        stats->closest_rays = closest;
         stats->shadow_rays = ps->h_counters->shadow_rays;
         stats->nan_samples = ps->h_counters->nan_samples;
         stats->iterations = iterations;
@@ -486,8 +619,31 @@ void cray_pool_release(cray_scene* sc) {
     if (ps->d_counters) cudaFree(ps->d_counters);
     if (ps->h_counters) cudaFreeHost(ps->h_counters);
     if (ps->d_film) cudaFree(ps->d_film);
+    if (ps->d_trace_counters) cudaFree(ps->d_trace_counters);
     delete ps;
     sc->pool = nullptr;
+}
+
+static int launch_trace(cray_scene* sc, int mode, bool any, const cray_ray* d_rays, uint64_t n, cray_hit* d_hits, cray_surface* d_surf, uint8_t* d_occluded, cudaStream_t stream) {
+    CRAY_CUDA(cudaSetDevice(sc->device));
+    if (mode == CRAY_TRAVERSE_EXACT) {
+        const uint64_t blocks = (n + 127) / 128;
+        if (any) k_trace_any_exact<<<(unsigned)blocks, 128, 0, stream>>>(sc->view, d_rays, n, d_occluded);
+        else k_trace_closest_exact<<<(unsigned)blocks, 128, 0, stream>>>(sc->view, d_rays, n, d_hits, d_surf);
+    } else {
+        int rc = ensure_pool(sc, 1);
+        if (rc != CRAY_OK) return rc;
+        auto* ps = static_cast<PoolStorage*>(sc->pool);
+        if (!ps->d_trace_counters) CRAY_CUDA(cudaMalloc(&ps->d_trace_counters, 2 * sizeof(unsigned long long)));
+        const unsigned long long init[2] = {n, 0ull};
+        CRAY_CUDA(cudaMemcpyAsync(ps->d_trace_counters, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+        const RayArraySource src{d_rays, d_hits, d_surf, d_occluded};
+        const unsigned blocks = (unsigned)std::min<uint64_t>(ps->persistent_blocks, (n + 127) / 128);
+        if (any) k_wide_persistent<true, RayArraySource><<<blocks, 128, 0, stream>>>(sc->view, src, ps->d_trace_counters, ps->d_trace_counters + 1);
+        else k_wide_persistent<false, RayArraySource><<<blocks, 128, 0, stream>>>(sc->view, src, ps->d_trace_counters, ps->d_trace_counters + 1);
+    }
+    CRAY_CUDA(cudaGetLastError());
+    return CRAY_OK;
 }
 
 int cray_trace_closest_device(cray_scene* sc, int mode, const cray_ray* d_rays, uint64_t n, cray_hit* d_hits, cray_surface* d_surf, void* stream) {
@@ -495,11 +651,7 @@ int cray_trace_closest_device(cray_scene* sc, int mode, const cray_ray* d_rays, 
     if (rc != CRAY_OK) return rc;
     if (n == 0) return CRAY_OK;
     if (!d_rays || !d_hits) { set_error("null buffer"); return CRAY_E_INVALID; }
-    CRAY_CUDA(cudaSetDevice(sc->device));
-    const uint64_t blocks = (n + 127) / 128;
-    k_trace_closest<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(sc->view, mode == CRAY_TRAVERSE_EXACT, d_rays, n, d_hits, d_surf);
-    CRAY_CUDA(cudaGetLastError());
-    return CRAY_OK;
+    return launch_trace(sc, mode, false, d_rays, n, d_hits, d_surf, nullptr, (cudaStream_t)stream);
 }
 
 int cray_trace_any_device(cray_scene* sc, int mode, const cray_ray* d_rays, uint64_t n, uint8_t* d_occluded, void* stream) {
@@ -507,11 +659,7 @@ int cray_trace_any_device(cray_scene* sc, int mode, const cray_ray* d_rays, uint
     if (rc != CRAY_OK) return rc;
     if (n == 0) return CRAY_OK;
     if (!d_rays || !d_occluded) { set_error("null buffer"); return CRAY_E_INVALID; }
-    CRAY_CUDA(cudaSetDevice(sc->device));
-    const uint64_t blocks = (n + 127) / 128;
-    k_trace_any<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(sc->view, mode == CRAY_TRAVERSE_EXACT, d_rays, n, d_occluded);
-    CRAY_CUDA(cudaGetLastError());
-    return CRAY_OK;
+    return launch_trace(sc, mode, true, d_rays, n, nullptr, nullptr, d_occluded, (cudaStream_t)stream);
 }
 
 int cray_trace_closest(cray_scene* sc, int mode, const cray_ray* rays, uint64_t n, cray_hit* hits, cray_surface* surf) {
