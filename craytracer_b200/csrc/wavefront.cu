@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -152,11 +153,13 @@ struct RayArraySource {  // S3: caller-provided cray_ray records
 //   prim    lanes with queued leaf primitives test ONE of them in f64 -- but only when at least kPrimLanes lanes have
 //           such work or some lane has nothing else left to do, so the f64 phase runs with many lanes at once
 //   advance pop stacks; finished lanes write their result and become idle
-constexpr int kRefillLanes = 8;
-constexpr int kPrimLanes = 10;
+struct WideTuning {
+    int refill_lanes;  // refill once this many lanes are idle
+    int prim_lanes;    // run the primitive phase once this many lanes have queued primitives
+};
 
 template <bool ANY, class Source>
-__global__ void __launch_bounds__(128) k_wide_persistent(SceneView s, Source src, const unsigned long long* __restrict__ n_ptr, unsigned long long* cursor) {
+__global__ void __launch_bounds__(128) k_wide_persistent(SceneView s, Source src, const unsigned long long* __restrict__ n_ptr, unsigned long long* cursor, WideTuning tune) {
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long n = *n_ptr;
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(128) k_wide_persistent(SceneView s, Source src
     bool exhausted = false;
     for (;;) {
         const unsigned idle = __ballot_sync(FULL, !t.live);
-        if (!exhausted && (idle == FULL || __popc(idle) >= kRefillLanes)) {
+        if (!exhausted && (idle == FULL || __popc(idle) >= tune.refill_lanes)) {
             const int want = __popc(idle);
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(cursor, (unsigned long long)want);
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(128) k_wide_persistent(SceneView s, Source src
         const unsigned prim_lanes = __ballot_sync(FULL, wants_prim);
         const unsigned starved = __ballot_sync(FULL, wants_prim && !t.has_node_work());
         bool finished = false;
-        if (wants_prim && (starved != 0u || __popc(prim_lanes) >= kPrimLanes)) finished = t.prim_step(s);
+        if (wants_prim && (starved != 0u || __popc(prim_lanes) >= tune.prim_lanes)) finished = t.prim_step(s);
         if (t.live) {
             if constexpr (ANY) {
                 if (finished) { src.store(s, id, true); t.live = false; }
@@ -497,6 +500,7 @@ struct PoolStorage {
     double* d_film = nullptr;
     uint64_t film_elems = 0;
     unsigned persistent_blocks = 0;   // SMs x resident CTAs of the persistent traversal kernel
+    WideTuning tune{8, 10};
     unsigned long long* d_trace_counters = nullptr;  // {n, cursor} for the S3 entry points
 };
 
@@ -511,6 +515,9 @@ int ensure_pool(cray_scene* sc, uint32_t capacity) {
         int per_sm = 0;
         CRAY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wide_persistent<false, ExtendSource>, 128, 0));
         ps->persistent_blocks = (unsigned)(sms * std::max(per_sm, 1));
+        if (const char* e = std::getenv("CRAY_REFILL_LANES")) ps->tune.refill_lanes = std::max(1, std::min(32, std::atoi(e)));
+        if (const char* e = std::getenv("CRAY_PRIM_LANES")) ps->tune.prim_lanes = std::max(1, std::min(32, std::atoi(e)));
+        if (const char* e = std::getenv("CRAY_BLOCKS_PER_SM")) ps->persistent_blocks = (unsigned)(sms * std::max(1, std::atoi(e)));
     }
     if (ps->pool.capacity >= capacity) return CRAY_OK;
     if (ps->slab) { cudaFree(ps->slab); ps->slab = nullptr; }
@@ -565,12 +572,12 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
         const bool timed = stats != nullptr;
         if (timed) CRAY_CUDA(cudaEventRecord(t0, stream));
         if (job.exact) k_extend_exact<<<g_live, 128, 0, stream>>>(sc->view, pool, &dc->n_extend);
-        else k_wide_persistent<false, ExtendSource><<<gp, 128, 0, stream>>>(sc->view, ExtendSource{pool}, &dc->n_extend, &dc->extend_cursor);
+        else k_wide_persistent<false, ExtendSource><<<gp, 128, 0, stream>>>(sc->view, ExtendSource{pool}, &dc->n_extend, &dc->extend_cursor, ps->tune);
         if (timed) CRAY_CUDA(cudaEventRecord(t1, stream));
         k_shade<<<g_live, 128, 0, stream>>>(sc->view, pool, job, dc);
         // at most one shadow ray per shaded vertex; the queue length lives on the device
         if (job.exact) k_shadow_exact<<<g_live, 128, 0, stream>>>(sc->view, pool, &dc->n_shadow);
-        else k_wide_persistent<true, ShadowSource><<<gp, 128, 0, stream>>>(sc->view, ShadowSource{pool}, &dc->n_shadow, &dc->shadow_cursor);
+        else k_wide_persistent<true, ShadowSource><<<gp, 128, 0, stream>>>(sc->view, ShadowSource{pool}, &dc->n_shadow, &dc->shadow_cursor, ps->tune);
         launches += 3;
         iterations += 1;
         if (timed) {
@@ -639,8 +646,8 @@ static int launch_trace(cray_scene* sc, int mode, bool any, const cray_ray* d_ra
         CRAY_CUDA(cudaMemcpyAsync(ps->d_trace_counters, init, sizeof(init), cudaMemcpyHostToDevice, stream));
         const RayArraySource src{d_rays, d_hits, d_surf, d_occluded};
         const unsigned blocks = (unsigned)std::min<uint64_t>(ps->persistent_blocks, (n + 127) / 128);
-        if (any) k_wide_persistent<true, RayArraySource><<<blocks, 128, 0, stream>>>(sc->view, src, ps->d_trace_counters, ps->d_trace_counters + 1);
-        else k_wide_persistent<false, RayArraySource><<<blocks, 128, 0, stream>>>(sc->view, src, ps->d_trace_counters, ps->d_trace_counters + 1);
+        if (any) k_wide_persistent<true, RayArraySource><<<blocks, 128, 0, stream>>>(sc->view, src, ps->d_trace_counters, ps->d_trace_counters + 1, ps->tune);
+        else k_wide_persistent<false, RayArraySource><<<blocks, 128, 0, stream>>>(sc->view, src, ps->d_trace_counters, ps->d_trace_counters + 1, ps->tune);
     }
     CRAY_CUDA(cudaGetLastError());
     return CRAY_OK;
