@@ -143,9 +143,10 @@ def lib():
     """Load libcray_b200.so (once).  Raises if it has not been built: there is no fallback path."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise ImportError(f"{LIB_PATH} is missing: build the CUDA library first (__graft_entry__.build() or make -C craytracer_b200/csrc)")
-        handle = C.CDLL(LIB_PATH)
+        path = os.environ.get("CRAY_B200_LIB", LIB_PATH)  # tuning builds (make VARIANT=...) sit beside the default library
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is missing: build the CUDA library first (__graft_entry__.build() or make -C craytracer_b200/csrc)")
+        handle = C.CDLL(path)
         for table in (SIGNATURES, EXTRA_SIGNATURES):
             for name, (restype, argtypes) in table.items():
                 fn = getattr(handle, name)

@@ -279,19 +279,41 @@ float float_down(double x) {
     return f;
 }
 
+struct Kid {
+    uint32_t id;     // is_prim: primitive index; else binary node index
+    bool is_prim;
+    Box3 box;
+};
+
 struct Collapser {
+    const cray_scene_desc& desc;
     const RefBvh& ref;
     WideBvh& out;
     uint32_t max_depth = 0;
 
-    void emit(uint32_t wide_idx, const std::vector<uint32_t>& kids, const Box3& node_box, uint32_t depth) {
+    Kid node_kid(uint32_t bin) const {
+        const BinNode& n = ref.nodes[bin];
+        if (n.axis == 3 && n.b == 1) {  // a one-primitive leaf is just that primitive
+            const uint32_t prim = ref.prim_order[n.a];
+            return {prim, true, primitive_bounds(desc, prim)};
+        }
+        return {bin, false, n.box};
+    }
+    // how many slots opening this kid adds
+    int growth(const Kid& k) const {
+        if (k.is_prim) return -1;  // cannot be opened
+        const BinNode& n = ref.nodes[k.id];
+        return n.axis == 3 ? (int)n.b - 1 : 1;
+    }
+
+    void emit(uint32_t wide_idx, const std::vector<Kid>& kids, const Box3& node_box, uint32_t depth) {
         max_depth = std::max(max_depth, depth);
         const int k = (int)kids.size();
         // slot assignment: slot bits (x=4, y=2, z=1) set = child sits on the + side of the node centre on that axis
         const V3 nc = box_centroid(node_box);
         double cost[8][8];
         for (int c = 0; c < k; ++c) {
-            const V3 dc = box_centroid(ref.nodes[kids[c]].box) - nc;
+            const V3 dc = box_centroid(kids[c].box) - nc;
             for (int s = 0; s < 8; ++s) cost[c][s] = ((s & 4) ? dc.x : -dc.x) + ((s & 2) ? dc.y : -dc.y) + ((s & 1) ? dc.z : -dc.z);
         }
         int slot_of[8], child_in[8];
@@ -328,58 +350,72 @@ struct Collapser {
         }
         w.ex = (uint8_t)(e[0] + 127); w.ey = (uint8_t)(e[1] + 127); w.ez = (uint8_t)(e[2] + 127);
         w.prim_base = (uint32_t)out.prim_order.size();
-        std::vector<uint32_t> interior_kids;
-        uint32_t prim_off = 0;
+        std::vector<Kid> interior_kids;
         for (int s = 0; s < 8; ++s) {
             const int c = child_in[s];
-            if (c < 0) { w.meta[s] = 0; continue; }
-            const BinNode& bn = ref.nodes[kids[c]];
+            if (c < 0) continue;
+            const Kid& kid = kids[c];
             for (int ax = 0; ax < 3; ++ax) {
-                double ql = std::floor((bn.box.lo[ax] - (double)p[ax]) / scale[ax]);
-                double qh = std::ceil((bn.box.hi[ax] - (double)p[ax]) / scale[ax]);
-                while (ql > 0.0 && (double)p[ax] + ql * scale[ax] > bn.box.lo[ax]) ql -= 1.0;
-                while (qh < 255.0 && (double)p[ax] + qh * scale[ax] < bn.box.hi[ax]) qh += 1.0;
+                double ql = std::floor((kid.box.lo[ax] - (double)p[ax]) / scale[ax]);
+                double qh = std::ceil((kid.box.hi[ax] - (double)p[ax]) / scale[ax]);
+                while (ql > 0.0 && (double)p[ax] + ql * scale[ax] > kid.box.lo[ax]) ql -= 1.0;
+                while (qh < 255.0 && (double)p[ax] + qh * scale[ax] < kid.box.hi[ax]) qh += 1.0;
                 ql = std::max(0.0, std::min(255.0, ql));
                 qh = std::max(0.0, std::min(255.0, qh));
                 w.qlo[ax][s] = (uint8_t)ql;
                 w.qhi[ax][s] = (uint8_t)qh;
             }
-            if (bn.axis == 3) {
-                w.meta[s] = (uint8_t)((bn.b << 5) | prim_off);
-                for (uint32_t i = 0; i < bn.b; ++i) out.prim_order.push_back(ref.prim_order[bn.a + i]);
-                prim_off += bn.b;
+            if (kid.is_prim) {
+                w.leafmask |= (uint8_t)(1u << s);
+                out.prim_order.push_back(kid.id);
             } else {
-                w.meta[s] = 0xE0;
                 w.imask |= (uint8_t)(1u << s);
-                interior_kids.push_back(kids[c]);
+                interior_kids.push_back(kid);
             }
         }
         w.child_base = (uint32_t)out.nodes.size();
         out.nodes[wide_idx] = w;
         const uint32_t base = (uint32_t)out.nodes.size();
         out.nodes.resize(out.nodes.size() + interior_kids.size());
-        for (size_t i = 0; i < interior_kids.size(); ++i) expand(base + (uint32_t)i, interior_kids[i], depth + 1);
+        for (size_t i = 0; i < interior_kids.size(); ++i) expand(base + (uint32_t)i, interior_kids[i].id, depth + 1);
     }
 
-    // Open the binary subtree rooted at interior node `bin` into up to 8 children (largest surface area first).
+    // Open the binary subtree rooted at `bin` into up to 8 children, largest surface area first.  Opening an
+    // interior node adds one child; opening a leaf of n primitives adds n - 1 (each primitive gets its own slot).
     void expand(uint32_t wide_idx, uint32_t bin, uint32_t depth) {
-        std::vector<uint32_t> kids;
+        std::vector<Kid> kids;
         const BinNode& root = ref.nodes[bin];
-        if (root.axis == 3) kids.push_back(bin);
-        else { kids.push_back(root.a); kids.push_back(root.b); }
-        while (kids.size() < 8) {
+        if (root.axis == 3) {
+            for (uint32_t i = 0; i < root.b; ++i) {
+                const uint32_t prim = ref.prim_order[root.a + i];
+                kids.push_back({prim, true, primitive_bounds(desc, prim)});
+            }
+        } else {
+            kids.push_back(node_kid(root.a));
+            kids.push_back(node_kid(root.b));
+        }
+        for (;;) {
             int pick = -1;
             double best = -1.0;
             for (size_t i = 0; i < kids.size(); ++i) {
-                const BinNode& c = ref.nodes[kids[i]];
-                if (c.axis == 3) continue;
-                const double sa = box_surface_area(c.box);
+                const int g = growth(kids[i]);
+                if (g < 0 || kids.size() + (size_t)g > 8) continue;
+                const double sa = box_surface_area(kids[i].box);
                 if (sa > best) { best = sa; pick = (int)i; }
             }
             if (pick < 0) break;
-            const BinNode c = ref.nodes[kids[pick]];
-            kids[pick] = c.a;
-            kids.push_back(c.b);
+            const BinNode c = ref.nodes[kids[pick].id];
+            if (c.axis == 3) {
+                const uint32_t first = ref.prim_order[c.a];
+                kids[pick] = {first, true, primitive_bounds(desc, first)};
+                for (uint32_t i = 1; i < c.b; ++i) {
+                    const uint32_t prim = ref.prim_order[c.a + i];
+                    kids.push_back({prim, true, primitive_bounds(desc, prim)});
+                }
+            } else {
+                kids[pick] = node_kid(c.a);
+                kids.push_back(node_kid(c.b));
+            }
         }
         emit(wide_idx, kids, root.box, depth);
     }
@@ -387,12 +423,12 @@ struct Collapser {
 
 }  // namespace
 
-void collapse_to_wide(const RefBvh& ref, WideBvh& out) {
+void collapse_to_wide(const cray_scene_desc& d, const RefBvh& ref, WideBvh& out) {
     out = WideBvh{};
     out.nodes.reserve(ref.nodes.size() / 4 + 16);
     out.prim_order.reserve(ref.prim_order.size());
     out.nodes.resize(1);
-    Collapser c{ref, out};
+    Collapser c{d, ref, out};
     c.expand(0, 0, 1);
     out.depth = c.max_depth;
 }

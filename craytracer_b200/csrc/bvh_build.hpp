@@ -5,7 +5,9 @@
 //    an exact-t tie.  Sub-trees are built by a thread pool (the tree is deterministic, the order of
 //    construction is not observable).
 //  * collapse_to_wide: greedy surface-area collapse of that tree into the GPU's 8-wide node format with
-//    8-bit quantised child boxes (conservatively rounded outward) and octant-ordered child slots.
+//    8-bit quantised child boxes (conservatively rounded outward) and octant-ordered child slots.  Leaves of
+//    the binary tree are opened too: a leaf slot of a wide node holds exactly ONE primitive with its own
+//    quantised box, so the f64 primitive test only runs on primitives whose own box the ray enters.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -34,23 +36,26 @@ struct RefBvh {
 Box3 primitive_bounds(const cray_scene_desc& d, uint64_t prim);
 void build_reference_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads = 0);
 
-struct alignas(16) WideNode {  // 80 B
+struct alignas(16) WideNode {  // 80 B: five 16-byte loads
     float px, py, pz;          // quantisation frame origin
     uint8_t ex, ey, ez;        // per-axis scale = 2^(e - 127) (raw f32 exponent field)
     uint8_t imask;             // bit s: slot s holds an interior child
     uint32_t child_base;       // first interior child (children contiguous, ascending slot)
-    uint32_t prim_base;        // first leaf primitive of this node in wide leaf order
-    uint8_t meta[8];           // slot: 0 empty | 0xE0 interior | (count 1..4) << 5 | offset (0..28) from prim_base
+    uint32_t prim_base;        // first primitive of this node in wide leaf order (primitives contiguous, ascending slot)
+    uint8_t leafmask;          // bit s: slot s holds exactly one primitive
+    uint8_t _pad[7];
     uint8_t qlo[3][8];         // quantised child box minima  [axis][slot]
     uint8_t qhi[3][8];         // quantised child box maxima
 };
 static_assert(sizeof(WideNode) == 80, "WideNode layout");
+
+constexpr int kWideStackLimit = 24;  // traversal stack entries per ray (traverse.cuh): one per level
 
 struct WideBvh {
     std::vector<WideNode> nodes;
     std::vector<uint32_t> prim_order;  // wide leaf order -> primitive index
     uint32_t depth = 0;
 };
-void collapse_to_wide(const RefBvh& ref, WideBvh& out);
+void collapse_to_wide(const cray_scene_desc& d, const RefBvh& ref, WideBvh& out);
 
 }  // namespace cray

@@ -126,15 +126,15 @@ void cray_debug_camera_matrices(const cray_camera_desc* c, double* out32) {
 }
 
 // Structural check of the 8-wide BVH against the reference binary tree it was collapsed from (host only):
-// every primitive exactly once, every quantised child box encloses the exact f64 box of the subtree it stands for,
-// leaf children keep the reference's leaf contents and order.  out[0..3] = wide nodes, depth, interior children, leaf children.
+// every primitive exactly once, every quantised child box encloses the exact f64 box of the subtree (or the single
+// primitive) it stands for.  out[0..3] = wide nodes, depth, interior children, leaf children.
 int cray_debug_check_wide_bvh(const cray_scene_desc* desc, uint64_t* out4) {
     using namespace cray;
     RefBvh ref;
     build_reference_bvh(*desc, ref);
     if (!ref.error.empty()) { set_error(ref.error); return CRAY_E_BVH; }
     WideBvh wide;
-    collapse_to_wide(ref, wide);
+    collapse_to_wide(*desc, ref, wide);
     std::vector<uint32_t> seen(desc->n_primitives, 0);
     for (uint32_t p : wide.prim_order) {
         if (p >= desc->n_primitives) { set_error("wide order references a missing primitive"); return CRAY_E_INVALID; }
@@ -155,23 +155,21 @@ int cray_debug_check_wide_bvh(const cray_scene_desc* desc, uint64_t* out4) {
         const double sc[3] = {std::ldexp(1.0, (int)w.ex - 127), std::ldexp(1.0, (int)w.ey - 127), std::ldexp(1.0, (int)w.ez - 127)};
         bool any = false;
         Box3 acc{};
-        uint32_t child = w.child_base;
+        uint32_t child = w.child_base, prim = w.prim_base;
+        if (w.imask & w.leafmask) { set_error("slot marked both interior and leaf"); return CRAY_E_INVALID; }
         for (int s = 0; s < 8; ++s) {
-            if (w.meta[s] == 0) continue;
+            const bool is_interior = (w.imask >> s) & 1, is_leaf = (w.leafmask >> s) & 1;
+            if (!is_interior && !is_leaf) continue;
             Box3 exact{};
-            if (w.meta[s] == 0xE0) {
-                if (!((w.imask >> s) & 1)) { set_error("interior child without imask bit"); return CRAY_E_INVALID; }
+            if (is_interior) {
                 if (child <= ni || child >= wide.nodes.size() || !done[child]) { set_error("bad child index"); return CRAY_E_INVALID; }
                 exact = node_box[child];
                 child += 1;
                 interior += 1;
             } else {
-                const uint32_t count = w.meta[s] >> 5, off = w.meta[s] & 31u;
-                if (count < 1 || count > 4) { set_error("bad leaf count"); return CRAY_E_INVALID; }
-                for (uint32_t k = 0; k < count; ++k) {
-                    const Box3 pb = primitive_bounds(*desc, wide.prim_order[w.prim_base + off + k]);
-                    exact = k == 0 ? pb : box_union(exact, pb);
-                }
+                if (prim >= wide.prim_order.size()) { set_error("bad primitive index"); return CRAY_E_INVALID; }
+                exact = primitive_bounds(*desc, wide.prim_order[prim]);
+                prim += 1;
                 leaves += 1;
             }
             const double qlo[3] = {p[0] + w.qlo[0][s] * sc[0], p[1] + w.qlo[1][s] * sc[1], p[2] + w.qlo[2][s] * sc[2]};

@@ -208,8 +208,9 @@ int cray_scene_create(const cray_scene_desc* d, int device, uint32_t build_flags
     if (!ref.error.empty()) { set_error(ref.error); return CRAY_E_BVH; }
     WideBvh wide;
     if (build_flags & CRAY_BUILD_FAST) {
-        collapse_to_wide(ref, wide);
-        if (wide.depth >= (uint32_t)30) { set_error("wide BVH deeper than the traversal stack"); return CRAY_E_BVH; }
+        collapse_to_wide(*d, ref, wide);
+        if (wide.depth >= (uint32_t)kWideStackLimit) { set_error("wide BVH deeper than the traversal stack"); return CRAY_E_BVH; }
+        if (d->n_primitives >= (1ull << 27)) { set_error("more than 2^27 primitives: the fast traversal's queue entries hold 27-bit leaf slots"); return CRAY_E_UNSUPPORTED; }
     }
     const double build_ms = ms_since(t0);
     t0 = std::chrono::steady_clock::now();

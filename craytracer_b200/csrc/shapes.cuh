@@ -11,12 +11,14 @@ struct Hit {
     uint32_t slot;    // index into the leaf-ordered LeafPrim array that was traversed, CRAY_NO_HIT = miss
 };
 
+// Five 16-byte read-only loads straight into registers (no round trip through a local-memory copy of the record).
 __device__ __forceinline__ LeafPrim load_leaf_prim(const LeafPrim* p) {
+    const double2* src = reinterpret_cast<const double2*>(p);
+    const double2 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), e = __ldg(src + 3), f = __ldg(src + 4);
     LeafPrim r;
-    const int4* src = reinterpret_cast<const int4*>(p);
-    int4* dst = reinterpret_cast<int4*>(&r);
-#pragma unroll
-    for (int i = 0; i < 5; ++i) dst[i] = __ldg(src + i);
+    r.d[0] = a.x; r.d[1] = a.y; r.d[2] = b.x; r.d[3] = b.y; r.d[4] = c.x; r.d[5] = c.y; r.d[6] = e.x; r.d[7] = e.y; r.d[8] = f.x;
+    r.prim = (uint32_t)__double2loint(f.y);
+    r.kind = (uint32_t)__double2hiint(f.y);
     return r;
 }
 

@@ -5,17 +5,18 @@
 //    Bounds::contains, near/far push order by sign of dir[split_axis], strict `t < max_distance` acceptance.
 //    Results are bit-identical to the reference by construction (including its false box misses).
 //
-//  traverse_wide<ANY>: production traversal of the 8-wide quantised BVH.  Boxes are tested in f32 with every
-//    rounding error pushed outward (see "conservative slab test" below) so no primitive the exact f64 leaf test
-//    would accept is ever culled; leaves run the same f64 primitive tests as the exact mode.  Among primitives
-//    with bit-equal t the one the reference would have visited first wins (reference_visits_first).
+//  Wide traversal (production): the 8-wide quantised BVH.  Boxes are tested in f32 with every rounding error
+//    pushed outward (see "conservative slab test" below) so no primitive the exact f64 test would accept is ever
+//    culled; the primitives whose own quantised box the ray enters are queued per warp and tested in f64 by all
+//    32 lanes at once (WarpShared, prim_round_*).  Among primitives with bit-equal t the one the reference would
+//    have visited first wins (reference_visits_first).
 #pragma once
 #include "shapes.cuh"
 
 namespace cray {
 
 constexpr int kExactStack = 96;
-constexpr int kWideStack = 32;
+constexpr int kWideStack = kWideStackLimit;   // node groups: at most one entry per level, the builder rejects deeper trees
 
 template <bool ANY>
 __device__ __forceinline__ bool traverse_exact(const SceneView& s, V3 o, V3 dir, double ray_max, Hit& hit) {
@@ -76,25 +77,31 @@ __device__ __noinline__ bool reference_visits_first(const SceneView& s, uint32_t
 // ---- conservative f32 slab test against 8 quantised child boxes -------------------------------------------------
 //
 // True entry/exit distance of a plane c = p + q*2^e along one axis: t = (c - o) / d.  The kernel evaluates
-//   t~ = fma(q, A, B),  A = 2^e * idir32,  B = (p - o32) * idir32
-// whose error is bounded by  |B|*2^-22 (rounding of p - o32 and of the product)  +  |o|*2^-23*|idir| (o rounded
-// to f32)  + a relative 2^-22 of t~ (rounding of idir32 = RN(1/d) and of the fma).  The first two are subtracted
-// from B for entry planes and added for exit planes once per node; the relative term is applied by scaling A and
-// B by (1 -+ 2^-21).  Child boxes themselves are rounded outward when quantised (bvh_build.cpp).
+//   t~ = fma(K + q, A, B'),   A = 2^e * idir32,   B' = B - K*A,   B = (p - o32) * idir32,   K = 2^15
+// (K + q is what one PRMT makes of the byte q: the f32 bit pattern 0x47000000 | q << 8).  Absolute error sources:
+// rounding of p - o32 and of its product with idir32 (<= |B| * 2^-23), o rounded to f32 (<= |o| * 2^-24 * |idir|),
+// rounding of B - err and of B' (<= 2^-23 * (|B| + K|A|)).  Their sum, with margin,
+//   err = |B| * 2^-21 + |o32| * 2^-23 * |idir32| + |A| * 2^-7
+// is subtracted from B for entry planes and added for exit planes once per node and axis.  What remains is a relative
+// error of at most 2^-22 per distance (idir32 = RN(1/RN(d)), the final fma), covered by accepting a child when
+//   max(entry distances, 0) <= min(exit distances) * (1 + 2^-19)   and   <= tmax * (1 + 2^-19).
+// Child boxes themselves are rounded outward when quantised (bvh_build.cpp).
 struct WideRay {
     float ox, oy, oz;
     float idx, idy, idz;
-    float eox, eoy, eoz;   // |o| * 2^-23 * |idir|
-    float tmax;            // ray max distance rounded up
+    float eox, eoy, eoz;   // |o32| * 2^-23 * |idir32|
+    float tmax;            // (current max distance rounded up) * (1 + 2^-19)
     uint32_t octinv;       // 7 - octant, octant bit (4,2,1) set where dir (x,y,z) is negative
-    uint32_t negx, negy, negz;
 };
 
+constexpr float kSlabSlack = 1.0f + 1.9073486e-6f;  // 1 + 2^-19
+
 __device__ __forceinline__ float safe_rcp(double d) {
-    const double lim = 1e-25;
-    double a = fabs(d) < lim ? copysign(lim, d) : d;
-    return (float)(1.0 / a);
+    float f = (float)d;
+    if (fabsf(f) < 1e-25f) f = sign_negative(d) ? -1e-25f : 1e-25f;
+    return __frcp_rn(f);
 }
+__device__ __forceinline__ float slab_tmax(double ray_max) { return __fmul_ru(__double2float_ru(ray_max), kSlabSlack); }
 
 __device__ __forceinline__ WideRay make_wide_ray(V3 o, V3 dir, double ray_max) {
     WideRay r;
@@ -104,16 +111,15 @@ __device__ __forceinline__ WideRay make_wide_ray(V3 o, V3 dir, double ray_max) {
     r.eox = (fabsf(r.ox) * k + 1e-30f) * fabsf(r.idx);
     r.eoy = (fabsf(r.oy) * k + 1e-30f) * fabsf(r.idy);
     r.eoz = (fabsf(r.oz) * k + 1e-30f) * fabsf(r.idz);
-    r.tmax = __double2float_ru(ray_max);
-    r.negx = sign_negative(dir.x); r.negy = sign_negative(dir.y); r.negz = sign_negative(dir.z);
-    r.octinv = 7u - ((r.negx << 2) | (r.negy << 1) | r.negz);
+    r.tmax = slab_tmax(ray_max);
+    const uint32_t oct = ((uint32_t)sign_negative(dir.x) << 2) | ((uint32_t)sign_negative(dir.y) << 1) | (uint32_t)sign_negative(dir.z);
+    r.octinv = 7u - oct;
     return r;
 }
 
-// byte `sel` of word -> float(2^23 + byte) in one PRMT, then an exact subtraction of 2^23
-__device__ __forceinline__ float byte_to_float(uint32_t word, uint32_t sel) {
-    const uint32_t bits = __byte_perm(word, 0x4B000000u, 0x7650u | sel);
-    return __uint_as_float(bits) - 8388608.0f;
+// byte `sel` of word -> the f32 2^15 + byte, in one PRMT
+__device__ __forceinline__ float byte_to_float_k(uint32_t word, uint32_t sel) {
+    return __uint_as_float(__byte_perm(word, 0x47000000u, 0x7604u | (sel << 4)));
 }
 
 struct AxisPlanes {
@@ -121,150 +127,182 @@ struct AxisPlanes {
 };
 __device__ __forceinline__ AxisPlanes axis_planes(float p, float o, float id, float eo, uint32_t ebyte) {
     const float scale = __uint_as_float(ebyte << 23);
-    const float B = (p - o) * id;
-    const float err = fmaf(fabsf(B), 2.3841858e-7f /*2^-22*/, eo);
     AxisPlanes r;
     r.A = scale * id;   // exact: scale is a power of two
-    r.Bn = B - err;     // entry distances may only get smaller
-    r.Bf = B + err;     // exit distances only larger
+    const float B = (p - o) * id;
+    const float err = fmaf(fabsf(B), 4.7683716e-7f /*2^-21*/, fmaf(fabsf(r.A), 7.8125e-3f /*2^-7*/, eo));
+    const float KA = 32768.0f * r.A;  // exact
+    r.Bn = (B - err) - KA;  // entry distances may only get smaller
+    r.Bf = (B + err) - KA;  // exit distances only larger
     return r;
 }
 
-// Traversal state of one ray through the 8-wide BVH, advanced one step at a time so that the lanes of a warp can be
-// kept in the same phase (see run_wide_persistent in wavefront.cu):
-//   node_step  pop the nearest pending interior child, test its 8 quantised child boxes, queue the leaf primitives hit
-//   prim_step  run the f64 intersection test of ONE queued primitive
-//   advance    when both queues are empty, pop the traversal stack (or finish)
-// Leaf primitives are postponed (kept in `tg`, spilled to the stack when a newer group arrives) until enough lanes of
-// the warp have primitive work, which is what keeps the expensive f64 tests from running one lane at a time.
-template <bool ANY>
-struct WideTraversal {
-    V3 o, dir;
-    double ray_max;
-    WideRay r;
-    uint2 ng;          // node group: x = first interior child, y = hit bits (31..24, octant ordered) | imask (7..0)
-    uint2 tg;          // primitive group: x = first leaf primitive of the node, y = mask of primitives still to test
-    uint2 stack[kWideStack];
-    int sp;
-    Hit hit;
-    uint32_t best_prim;
-    bool live;
+// ---- per-warp shared state of the persistent traversal kernel -----------------------------------------------------------
+//
+// Each lane owns one ray.  Its f64 origin / direction and its current closest hit live here, so that ANY lane of the warp
+// can run a queued primitive test for it.  `queue` is a ring of pending tests (owner lane << 27 | leaf slot).
+constexpr uint32_t kQueue = 512;        // >= 31 left over + 32 lanes x 8 leaf slots pushed by one node phase
+constexpr uint32_t kSlotBits = 27;
+constexpr uint32_t kSlotMask = (1u << kSlotBits) - 1u;
 
-    __device__ __forceinline__ void begin(V3 origin, V3 direction, double max_distance) {
-        o = origin; dir = direction; ray_max = max_distance;
-        r = make_wide_ray(origin, direction, max_distance);
-        ng = make_uint2(0u, 0x80000000u);  // the root, as a one-child node group
-        tg = make_uint2(0u, 0u);
-        sp = 0;
-        hit.slot = CRAY_NO_HIT; hit.t = max_distance; hit.u = 0.0; hit.v = 0.0;
-        best_prim = 0;
-        live = true;
-    }
-    __device__ __forceinline__ bool has_node_work() const { return (ng.y & 0xFF000000u) != 0u; }
-    __device__ __forceinline__ bool has_prim_work() const { return tg.y != 0u; }
-
-    __device__ __forceinline__ void node_step(const SceneView& s) {
-        const uint32_t bit = 31u - __clz(ng.y);
-        ng.y &= ~(1u << bit);
-        const uint32_t slot = (bit - 24u) ^ r.octinv;
-        const uint32_t child = ng.x + __popc(ng.y & 0xFFu & ((1u << slot) - 1u));
-        if ((ng.y & 0xFF000000u) && sp < kWideStack) stack[sp++] = ng;
-
-        const int4* raw = reinterpret_cast<const int4*>(s.wide_nodes + child);
-        const int4 n0 = __ldg(raw), n1 = __ldg(raw + 1), n2 = __ldg(raw + 2), n3 = __ldg(raw + 3), n4 = __ldg(raw + 4);
-        // n0 = px, py, pz, {ex,ey,ez,imask};  n1 = child_base, prim_base, meta[0..3], meta[4..7]
-        // n2 = qlo_x[0..7], qlo_y[0..7];  n3 = qlo_z[0..7], qhi_x[0..7];  n4 = qhi_y[0..7], qhi_z[0..7]
-        const uint32_t e_imask = (uint32_t)n0.w;
-        const AxisPlanes X = axis_planes(__int_as_float(n0.x), r.ox, r.idx, r.eox, e_imask & 0xFFu);
-        const AxisPlanes Y = axis_planes(__int_as_float(n0.y), r.oy, r.idy, r.eoy, (e_imask >> 8) & 0xFFu);
-        const AxisPlanes Z = axis_planes(__int_as_float(n0.z), r.oz, r.idz, r.eoz, (e_imask >> 16) & 0xFFu);
-        const uint32_t imask = e_imask >> 24;
-        // entry planes: lower bounds for positive directions, upper bounds for negative ones
-        const uint32_t nx0 = r.negx ? (uint32_t)n3.z : (uint32_t)n2.x, nx1 = r.negx ? (uint32_t)n3.w : (uint32_t)n2.y;
-        const uint32_t fx0 = r.negx ? (uint32_t)n2.x : (uint32_t)n3.z, fx1 = r.negx ? (uint32_t)n2.y : (uint32_t)n3.w;
-        const uint32_t ny0 = r.negy ? (uint32_t)n4.x : (uint32_t)n2.z, ny1 = r.negy ? (uint32_t)n4.y : (uint32_t)n2.w;
-        const uint32_t fy0 = r.negy ? (uint32_t)n2.z : (uint32_t)n4.x, fy1 = r.negy ? (uint32_t)n2.w : (uint32_t)n4.y;
-        const uint32_t nz0 = r.negz ? (uint32_t)n4.z : (uint32_t)n3.x, nz1 = r.negz ? (uint32_t)n4.w : (uint32_t)n3.y;
-        const uint32_t fz0 = r.negz ? (uint32_t)n3.x : (uint32_t)n4.z, fz1 = r.negz ? (uint32_t)n3.y : (uint32_t)n4.w;
-        const uint32_t meta_lo = (uint32_t)n1.z, meta_hi = (uint32_t)n1.w;
-
-        uint32_t interior_hits = 0, prim_hits = 0;
-#pragma unroll
-        for (int sl = 0; sl < 8; ++sl) {
-            const uint32_t sel = sl & 3;
-            const uint32_t meta = ((sl < 4 ? meta_lo : meta_hi) >> (8 * sel)) & 0xFFu;
-            const float tnx = fmaf(byte_to_float(sl < 4 ? nx0 : nx1, sel), X.A, X.Bn);
-            const float tny = fmaf(byte_to_float(sl < 4 ? ny0 : ny1, sel), Y.A, Y.Bn);
-            const float tnz = fmaf(byte_to_float(sl < 4 ? nz0 : nz1, sel), Z.A, Z.Bn);
-            const float tfx = fmaf(byte_to_float(sl < 4 ? fx0 : fx1, sel), X.A, X.Bf);
-            const float tfy = fmaf(byte_to_float(sl < 4 ? fy0 : fy1, sel), Y.A, Y.Bf);
-            const float tfz = fmaf(byte_to_float(sl < 4 ? fz0 : fz1, sel), Z.A, Z.Bf);
-            // relative slack 2^-21 for the rounding of idir and of the fmas: shrink the (non-negative) entry
-            // distance, grow the exit distance (a negative exit distance only becomes more negative: still a miss)
-            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f)) * (1.0f - 4.7683716e-7f);
-            const float tf = fminf(fminf(fminf(tfx, tfy), tfz) * (1.0f + 4.7683716e-7f), r.tmax);
-            if (meta != 0u && tn <= tf) {
-                if (meta == 0xE0u) interior_hits |= 1u << (24u + ((uint32_t)sl ^ r.octinv));
-                else prim_hits |= ((1u << (meta >> 5)) - 1u) << (meta & 31u);
-            }
-        }
-        if (prim_hits) {
-            if (tg.y && sp < kWideStack) stack[sp++] = make_uint2(tg.x | 0x80000000u, tg.y);  // older group waits on the stack
-            tg = make_uint2((uint32_t)n1.y, prim_hits);
-        }
-        ng = make_uint2((uint32_t)n1.x, interior_hits | imask);
-    }
-
-    // Tests one queued primitive.  Returns true if the ray is finished by it (any-hit mode found an occluder).
-    __device__ __forceinline__ bool prim_step(const SceneView& s) {
-        const uint32_t k = __ffs(tg.y) - 1u;
-        tg.y &= tg.y - 1u;
-        const uint32_t slot = tg.x + k;
-        const LeafPrim lp = load_leaf_prim(s.wide_prims + slot);
-        if (ANY) return leaf_prim_any(s, lp, o, dir, ray_max);
-        double u, v;
-        const int verdict = leaf_prim_candidate(s, lp, o, dir, ray_max, hit.slot != CRAY_NO_HIT, u, v);
-        if (verdict == 1) {
-            hit.t = ray_max; hit.u = u; hit.v = v; hit.slot = slot;
-            best_prim = lp.prim;
-            r.tmax = __double2float_ru(ray_max);
-        } else if (verdict == 2 && lp.prim != best_prim) {
-            // exact-t tie: keep whichever primitive the reference's traversal order reaches first
-            if (reference_visits_first(s, s.rank_of_prim[lp.prim], s.rank_of_prim[best_prim], dir)) {
-                hit.u = u; hit.v = v; hit.slot = slot;
-                best_prim = lp.prim;
-            }
-        }
-        return false;
-    }
-
-    // Refill the work queues from the stack.  Returns true when the traversal is complete.
-    __device__ __forceinline__ bool advance() {
-        if (has_node_work() || has_prim_work()) return false;
-        if (sp == 0) return true;
-        const uint2 e = stack[--sp];
-        if (e.x & 0x80000000u) tg = make_uint2(e.x & 0x7FFFFFFFu, e.y);
-        else ng = e;
-        return false;
-    }
+struct WarpShared {
+    double ox[32], oy[32], oz[32], dx[32], dy[32], dz[32];
+    double tmax[32];      // closest-hit: distance of the best hit so far (ray.max_distance); any-hit: the ray's max distance
+    float tmax32[32];     // slab_tmax(tmax)
+    uint32_t best[32];    // closest-hit: leaf slot of the best hit, CRAY_NO_HIT if none; any-hit: 1 once occluded
+    uint32_t pend[32];    // queued tests of this lane's ray that have not run yet
+    uint32_t tail;        // entries pushed so far (ring position of the next push)
+    uint32_t _pad[3];
+    uint32_t queue[kQueue];
 };
 
-// Single-ray driver (no warp cooperation): used where only a handful of rays are traced.
-template <bool ANY>
-__device__ __forceinline__ bool traverse_wide(const SceneView& s, V3 o, V3 dir, double ray_max, Hit& hit) {
-    WideTraversal<ANY> t;
-    t.begin(o, dir, ray_max);
-    for (;;) {
-        if (t.has_prim_work()) {
-            if (t.prim_step(s)) return true;
-        } else if (t.has_node_work()) {
-            t.node_step(s);
-        } else if (t.advance()) {
-            break;
+__device__ __forceinline__ void warp_begin_ray(WarpShared& ws, unsigned lane, V3 o, V3 dir, double ray_max, uint32_t best_init) {
+    ws.ox[lane] = o.x; ws.oy[lane] = o.y; ws.oz[lane] = o.z;
+    ws.dx[lane] = dir.x; ws.dy[lane] = dir.y; ws.dz[lane] = dir.z;
+    ws.tmax[lane] = ray_max;
+    ws.tmax32[lane] = slab_tmax(ray_max);
+    ws.best[lane] = best_init;
+    ws.pend[lane] = 0u;
+}
+
+// One interior node for one ray: pops the nearest pending child of the node group `ng`, tests its 8 quantised child boxes,
+// leaves the interior children hit in `ng` (octant ordered) and queues the primitives whose box was hit.
+__device__ __forceinline__ void node_step(const SceneView& s, WarpShared& ws, unsigned lane, const WideRay& r, uint2& ng, uint2* stack, int& sp) {
+    const uint32_t bit = 31u - __clz(ng.y);
+    ng.y &= ~(1u << bit);
+    const uint32_t slot = (bit - 24u) ^ r.octinv;
+    const uint32_t child = ng.x + __popc(ng.y & 0xFFu & ((1u << slot) - 1u));
+    if ((ng.y & 0xFF000000u) && sp < kWideStack) stack[sp++] = ng;
+
+    const int4* raw = reinterpret_cast<const int4*>(s.wide_nodes + child);
+    const int4 n0 = __ldg(raw), n1 = __ldg(raw + 1), n2 = __ldg(raw + 2), n3 = __ldg(raw + 3), n4 = __ldg(raw + 4);
+    // n0 = px, py, pz, {ex,ey,ez,imask};  n1 = child_base, prim_base, {leafmask, pad}, pad
+    // n2 = qlo_x[0..7], qlo_y[0..7];  n3 = qlo_z[0..7], qhi_x[0..7];  n4 = qhi_y[0..7], qhi_z[0..7]
+    const uint32_t e_imask = (uint32_t)n0.w;
+    const AxisPlanes X = axis_planes(__int_as_float(n0.x), r.ox, r.idx, r.eox, e_imask & 0xFFu);
+    const AxisPlanes Y = axis_planes(__int_as_float(n0.y), r.oy, r.idy, r.eoy, (e_imask >> 8) & 0xFFu);
+    const AxisPlanes Z = axis_planes(__int_as_float(n0.z), r.oz, r.idz, r.eoz, (e_imask >> 16) & 0xFFu);
+    const uint32_t imask = e_imask >> 24, leafmask = (uint32_t)n1.z & 0xFFu;
+    // entry planes: lower bounds for positive directions, upper bounds for negative ones
+    const bool negx = !(r.octinv & 4u), negy = !(r.octinv & 2u), negz = !(r.octinv & 1u);
+    const uint32_t nx0 = negx ? (uint32_t)n3.z : (uint32_t)n2.x, nx1 = negx ? (uint32_t)n3.w : (uint32_t)n2.y;
+    const uint32_t fx0 = negx ? (uint32_t)n2.x : (uint32_t)n3.z, fx1 = negx ? (uint32_t)n2.y : (uint32_t)n3.w;
+    const uint32_t ny0 = negy ? (uint32_t)n4.x : (uint32_t)n2.z, ny1 = negy ? (uint32_t)n4.y : (uint32_t)n2.w;
+    const uint32_t fy0 = negy ? (uint32_t)n2.z : (uint32_t)n4.x, fy1 = negy ? (uint32_t)n2.w : (uint32_t)n4.y;
+    const uint32_t nz0 = negz ? (uint32_t)n4.z : (uint32_t)n3.x, nz1 = negz ? (uint32_t)n4.w : (uint32_t)n3.y;
+    const uint32_t fz0 = negz ? (uint32_t)n3.x : (uint32_t)n4.z, fz1 = negz ? (uint32_t)n3.y : (uint32_t)n4.w;
+
+    uint32_t hits = 0;
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl) {
+        const uint32_t sel = sl & 3;
+        const float tnx = fmaf(byte_to_float_k(sl < 4 ? nx0 : nx1, sel), X.A, X.Bn);
+        const float tny = fmaf(byte_to_float_k(sl < 4 ? ny0 : ny1, sel), Y.A, Y.Bn);
+        const float tnz = fmaf(byte_to_float_k(sl < 4 ? nz0 : nz1, sel), Z.A, Z.Bn);
+        const float tfx = fmaf(byte_to_float_k(sl < 4 ? fx0 : fx1, sel), X.A, X.Bf);
+        const float tfy = fmaf(byte_to_float_k(sl < 4 ? fy0 : fy1, sel), Y.A, Y.Bf);
+        const float tfz = fmaf(byte_to_float_k(sl < 4 ? fz0 : fz1, sel), Z.A, Z.Bf);
+        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+        const float tf = fminf(fminf(fminf(tfx, tfy), tfz) * kSlabSlack, r.tmax);
+        hits |= (tn <= tf ? 1u : 0u) << sl;
+    }
+    // interior children: bit of slot sl moves to position sl ^ octinv (nearest child in the highest bit)
+    uint32_t ih = hits & imask;
+    if (r.octinv & 1u) ih = ((ih & 0x55u) << 1) | ((ih & 0xAAu) >> 1);
+    if (r.octinv & 2u) ih = ((ih & 0x33u) << 2) | ((ih & 0xCCu) >> 2);
+    if (r.octinv & 4u) ih = ((ih & 0x0Fu) << 4) | ((ih & 0xF0u) >> 4);
+    ng = make_uint2((uint32_t)n1.x, (ih << 24) | imask);
+    // primitives: one per leaf slot, contiguous from prim_base in ascending slot order
+    uint32_t lh = hits & leafmask;
+    if (lh) {
+        const uint32_t n = __popc(lh);
+        uint32_t pos = atomicAdd(&ws.tail, n);
+        ws.pend[lane] += n;
+        const uint32_t tag = lane << kSlotBits, prim_base = (uint32_t)n1.y;
+        do {
+            const uint32_t k = __ffs(lh) - 1u;
+            lh &= lh - 1u;
+            ws.queue[pos & (kQueue - 1u)] = tag | (prim_base + __popc(leafmask & ((1u << k) - 1u)));
+            pos += 1u;
+        } while (lh);
+    }
+}
+
+// Runs the first min(count, 32) queued tests, one per lane (closest-hit flavour).  The lanes testing primitives for the same
+// ray form a group (__match_any_sync); the group's smallest distance, if it beats the ray's current one, becomes the new best.
+// Exact-t ties -- with the current best or inside the group -- take the slow path that asks which primitive the reference's
+// traversal reaches first.
+__device__ __forceinline__ void prim_round_closest(const SceneView& s, WarpShared& ws, unsigned lane, uint32_t head, uint32_t count) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const bool act = lane < count;
+    const uint32_t e = act ? ws.queue[(head + lane) & (kQueue - 1u)] : 0u;
+    const uint32_t owner = e >> kSlotBits, slot = e & kSlotMask;
+    int verdict = 0;
+    double t = 0.0;
+    uint32_t my_prim = 0;
+    V3 dir = mk(0.0, 0.0, 0.0);
+    if (act) {
+        const LeafPrim lp = load_leaf_prim(s.wide_prims + slot);
+        const V3 o = mk(ws.ox[owner], ws.oy[owner], ws.oz[owner]);
+        dir = mk(ws.dx[owner], ws.dy[owner], ws.dz[owner]);
+        const double rmax = ws.tmax[owner];
+        double cand = rmax, u, v;
+        verdict = leaf_prim_candidate(s, lp, o, dir, cand, ws.best[owner] != CRAY_NO_HIT, u, v);
+        t = verdict == 1 ? cand : rmax;
+        my_prim = lp.prim;
+    }
+    const unsigned grp = __match_any_sync(FULL, act ? owner : 32u + lane);
+    // accepted distances are positive f64: they order like their bit patterns
+    const uint32_t hi = verdict ? (uint32_t)__double2hiint(t) : 0x7FFFFFFFu;
+    const uint32_t hmin = __reduce_min_sync(grp, hi);
+    const uint32_t lo = (verdict && hi == hmin) ? (uint32_t)__double2loint(t) : 0xFFFFFFFFu;
+    const uint32_t lmin = __reduce_min_sync(grp, lo);
+    const bool win = verdict && hi == hmin && (uint32_t)__double2loint(t) == lmin;
+    const unsigned wins = __ballot_sync(FULL, win) & grp;
+    const bool tie = win && (__popc(wins) > 1 || verdict == 2);
+    if (win && !tie) {
+        ws.tmax[owner] = t;
+        ws.tmax32[owner] = slab_tmax(t);
+        ws.best[owner] = slot;
+    }
+    if (act && lane == (unsigned)(__ffs(grp) - 1)) ws.pend[owner] -= __popc(grp);
+    unsigned ties = __ballot_sync(FULL, tie);
+    while (ties) {
+        __syncwarp();
+        const unsigned l = __ffs(ties) - 1u;
+        ties &= ties - 1u;
+        if (lane == l) {
+            const uint32_t cur = ws.best[owner];
+            const double cur_t = ws.tmax[owner];
+            bool take = false;
+            if (cur == CRAY_NO_HIT || t < cur_t) take = true;
+            else if (t == cur_t && cur != slot)
+                take = reference_visits_first(s, s.rank_of_prim[my_prim], s.rank_of_prim[s.wide_prims[cur].prim], dir);
+            if (take) {
+                ws.tmax[owner] = t;
+                ws.tmax32[owner] = slab_tmax(t);
+                ws.best[owner] = slot;
+            }
         }
     }
-    hit = t.hit;
-    return hit.slot != CRAY_NO_HIT;
+    __syncwarp();
+}
+
+// Any-hit flavour: a test that finds an occluder marks the ray; tests queued for a ray already marked are skipped.
+__device__ __forceinline__ void prim_round_any(const SceneView& s, WarpShared& ws, unsigned lane, uint32_t head, uint32_t count) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const bool act = lane < count;
+    const uint32_t e = act ? ws.queue[(head + lane) & (kQueue - 1u)] : 0u;
+    const uint32_t owner = e >> kSlotBits, slot = e & kSlotMask;
+    if (act && ws.best[owner] == 0u) {
+        const LeafPrim lp = load_leaf_prim(s.wide_prims + slot);
+        const V3 o = mk(ws.ox[owner], ws.oy[owner], ws.oz[owner]);
+        const V3 dir = mk(ws.dx[owner], ws.dy[owner], ws.dz[owner]);
+        if (leaf_prim_any(s, lp, o, dir, ws.tmax[owner])) ws.best[owner] = 1u;
+    }
+    const unsigned grp = __match_any_sync(FULL, act ? owner : 32u + lane);
+    if (act && lane == (unsigned)(__ffs(grp) - 1)) ws.pend[owner] -= __popc(grp);
+    __syncwarp();
 }
 
 }  // namespace cray

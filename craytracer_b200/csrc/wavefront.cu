@@ -14,9 +14,12 @@
 //   shadow      any-hit traversal of the queued shadow rays, adds the unoccluded contributions
 // so all lanes keep working until the sample range is exhausted (path regeneration).
 //
-// Fast-mode traversal runs as a persistent kernel: every warp pulls rays from the queue with one atomic per refill,
-// steps its 32 traversals in lock-step (node phase, then primitive phase -- see WideTraversal) and refills idle lanes
-// once enough of them have finished, so SIMD lanes are not parked behind the longest ray of a fixed assignment.
+// Fast-mode traversal runs as a persistent kernel: every warp pulls rays from the queue with one atomic per refill and
+// steps its 32 traversals in lock-step.  Node phases test the 8 quantised child boxes of one interior node per lane (f32)
+// and push the primitives whose box was hit onto a per-warp queue in shared memory; as soon as 32 tests are queued the
+// whole warp runs them, one (ray, primitive) pair per lane, in f64 -- so the expensive exact tests always execute with
+// full SIMD width and 32 independent loads in flight.  Idle lanes are refilled once enough of them have finished, so no
+// lane is parked behind the longest ray of a fixed assignment.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -35,8 +38,8 @@ enum : uint32_t { SLOT_EMPTY = 0, SLOT_ACTIVE = 1, SLOT_DONE = 2 };
 struct Pool {  // structure-of-arrays over `capacity` path slots
     uint32_t capacity;
     double *ox, *oy, *oz, *dx, *dy, *dz;          // ray to extend (max_distance is always +inf: Ray::new)
-    double *hit_t, *hit_u, *hit_v;                 // result of k_extend
-    uint32_t* hit_slot;
+    double* hit_t;                                 // result of the extend stage: distance and leaf slot (CRAY_NO_HIT = miss);
+    uint32_t* hit_slot;                            // k_shade re-derives the barycentrics from them (same code, same bits)
     double *beta_r, *beta_g, *beta_b, *L_r, *L_g, *L_b, *prev_bsdf_pdf;
     double *sdx, *sdy, *sdz, *smax, *sc_r, *sc_g, *sc_b;  // pending shadow ray (origin = ox,oy,oz) and its contribution
     uint32_t *id, *pixel, *hash, *shuffled_rev;    // job-relative sample id, film offset, sampler state
@@ -79,10 +82,11 @@ struct ExtendSource {  // queued path rays -> Pool::hit_*
         ray_max = inf_f64();
         return i;
     }
-    __device__ __forceinline__ void store(const SceneView&, uint32_t i, const WideTraversal<false>& t) const {
-        p.hit_slot[i] = t.hit.slot;
-        p.hit_t[i] = t.hit.t; p.hit_u[i] = t.hit.u; p.hit_v[i] = t.hit.v;
+    __device__ __forceinline__ void store_closest(const SceneView&, uint32_t i, uint32_t slot, double t) const {
+        p.hit_slot[i] = slot;
+        p.hit_t[i] = t;
     }
+    __device__ __forceinline__ void store_any(uint32_t, bool) const {}
 };
 
 struct ShadowSource {  // queued shadow rays -> L += contribution when unoccluded (path_integrator.rs:141-163)
@@ -94,12 +98,14 @@ struct ShadowSource {  // queued shadow rays -> L += contribution when unocclude
         ray_max = p.smax[i];
         return i;
     }
-    __device__ __forceinline__ void store(const SceneView&, uint32_t i, bool occluded) const {
+    __device__ __forceinline__ void store_closest(const SceneView&, uint32_t, uint32_t, double) const {}
+    __device__ __forceinline__ void store_any(uint32_t i, bool occluded) const {
         if (!occluded) { p.L_r[i] += p.sc_r[i]; p.L_g[i] += p.sc_g[i]; p.L_b[i] += p.sc_b[i]; }
     }
 };
 
-__device__ __forceinline__ void write_hit(const SceneView& s, const LeafPrim* prims, const cray_ray& r, const Hit& h, bool found, uint64_t i,
+// `h.u, h.v` are only consulted when `have_uv`; otherwise a triangle's barycentrics are re-derived from (slot, t).
+__device__ __forceinline__ void write_hit(const SceneView& s, const LeafPrim* prims, const cray_ray& r, Hit h, bool have_uv, bool found, uint64_t i,
                                           cray_hit* hits, cray_surface* surf) {
     cray_hit out;
     out._pad = 0;
@@ -108,10 +114,14 @@ __device__ __forceinline__ void write_hit(const SceneView& s, const LeafPrim* pr
     if (found) {
         const V3 o = mk(r.origin[0], r.origin[1], r.origin[2]), d = mk(r.direction[0], r.direction[1], r.direction[2]);
         const LeafPrim lp = load_leaf_prim(prims + h.slot);
+        const bool tri = (lp.kind & 0xFFu) == PRIM_TRIANGLE;
+        if (tri && !have_uv) {
+            double t2;
+            triangle_eval(lp.d, o, d, t2, h.u, h.v);
+        }
         V3 loc, nrm;
         double tu, tv;
         surface_at(s, lp, o, d, h.t, h.u, h.v, loc, nrm, tu, tv);
-        const bool tri = (lp.kind & 0xFFu) == PRIM_TRIANGLE;
         out.prim = lp.prim;
         out.t = h.t;
         out.u = tri ? h.u : tu;  // triangles: Moeller-Trumbore barycentrics; spheres / disks: surface uv
@@ -139,68 +149,114 @@ struct RayArraySource {  // S3: caller-provided cray_ray records
         ray_max = r.max_distance;
         return (uint32_t)idx;
     }
-    __device__ __forceinline__ void store(const SceneView& s, uint32_t i, const WideTraversal<false>& t) const {
-        write_hit(s, s.wide_prims, rays[i], t.hit, t.hit.slot != CRAY_NO_HIT, i, hits, surf);
+    __device__ __forceinline__ void store_closest(const SceneView& s, uint32_t i, uint32_t slot, double t) const {
+        Hit h;
+        h.slot = slot; h.t = t; h.u = 0.0; h.v = 0.0;
+        write_hit(s, s.wide_prims, rays[i], h, false, slot != CRAY_NO_HIT, i, hits, surf);
     }
-    __device__ __forceinline__ void store(const SceneView&, uint32_t i, bool occ) const { occluded[i] = occ ? 1 : 0; }
+    __device__ __forceinline__ void store_any(uint32_t i, bool occ) const { occluded[i] = occ ? 1 : 0; }
 };
 
 // ---- persistent wide-BVH traversal ----------------------------------------------------------------------------------
 //
-// One warp = 32 concurrent traversals stepped in lock-step.  Per loop iteration:
-//   refill  if at least kRefillLanes lanes are idle (or all are), one atomicAdd claims that many queue entries
-//   node    lanes with a pending interior child visit it (8 quantised box tests, f32)
-//   prim    lanes with queued leaf primitives test ONE of them in f64 -- but only when at least kPrimLanes lanes have
-//           such work or some lane has nothing else left to do, so the f64 phase runs with many lanes at once
-//   advance pop stacks; finished lanes write their result and become idle
+// One warp = 32 concurrent traversals.  Per loop iteration:
+//   refill  if at least tune.refill_lanes lanes are idle (or all are), one atomicAdd claims that many queue entries
+//   node    every lane with a pending interior child visits it (node_step: 8 quantised box tests in f32, hit primitives
+//           are pushed onto the warp's queue)
+//   prims   while 32 tests are queued -- or fewer, when no lane has node work left or tune.wait_lanes lanes can do nothing
+//           but wait for their tests -- the warp runs them, one per lane (prim_round_*)
+//   finish  a lane whose node stack is empty and whose tests have all run writes its result and becomes idle
 struct WideTuning {
     int refill_lanes;  // refill once this many lanes are idle
-    int prim_lanes;    // run the primitive phase once this many lanes have queued primitives
+    int wait_lanes;    // run a partial primitive round once this many lanes are waiting on queued tests
 };
 
+#ifndef CRAY_WIDE_MIN_BLOCKS
+#define CRAY_WIDE_MIN_BLOCKS 5
+#endif
+constexpr int kWideMinBlocks = CRAY_WIDE_MIN_BLOCKS;   // CTAs of 128 threads per SM the register allocation is held to
+
+enum : int { LANE_IDLE = 0, LANE_LIVE = 1, LANE_DRAIN = 2 };
+
 template <bool ANY, class Source>
-__global__ void __launch_bounds__(128) k_wide_persistent(SceneView s, Source src, const unsigned long long* __restrict__ n_ptr, unsigned long long* cursor, WideTuning tune) {
+__global__ void __launch_bounds__(128, kWideMinBlocks) k_wide_persistent(SceneView s, Source src, const unsigned long long* __restrict__ n_ptr, unsigned long long* cursor, WideTuning tune) {
+    __shared__ WarpShared shared[4];
+    WarpShared& ws = shared[threadIdx.x >> 5];
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long n = *n_ptr;
-    WideTraversal<ANY> t;
-    t.live = false;
+    if (lane == 0) ws.tail = 0u;
+    ws.pend[lane] = 0u;
+    __syncwarp();
+    uint32_t head = 0;  // queue entries consumed so far (warp-uniform)
+    WideRay r;
+    uint2 ng = make_uint2(0u, 0u);
+    uint2 stack[kWideStack];
+    int sp = 0;
+    int state = LANE_IDLE;
     uint32_t id = 0;
     bool exhausted = false;
     for (;;) {
-        const unsigned idle = __ballot_sync(FULL, !t.live);
+        const unsigned idle = __ballot_sync(FULL, state == LANE_IDLE);
         if (!exhausted && (idle == FULL || __popc(idle) >= tune.refill_lanes)) {
             const int want = __popc(idle);
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(cursor, (unsigned long long)want);
             base = __shfl_sync(FULL, base, 0);
-            if (!t.live) {
+            if (state == LANE_IDLE) {
                 const unsigned long long idx = base + __popc(idle & ((1u << lane) - 1u));
                 if (idx < n) {
                     V3 o, d;
                     double ray_max;
                     id = src.load(idx, o, d, ray_max);
-                    t.begin(o, d, ray_max);
+                    r = make_wide_ray(o, d, ray_max);
+                    warp_begin_ray(ws, lane, o, d, ray_max, ANY ? 0u : CRAY_NO_HIT);
+                    ng = make_uint2(0u, 0x80000000u);  // the root, as a one-child node group
+                    sp = 0;
+                    state = LANE_LIVE;
                 }
             }
             if (base + want >= n) exhausted = true;
         }
-        if (__ballot_sync(FULL, t.live) == 0u) {
+        if (__ballot_sync(FULL, state != LANE_IDLE) == 0u) {
             if (exhausted) break;
             continue;
         }
-        if (t.live && t.has_node_work()) t.node_step(s);
-        const bool wants_prim = t.live && t.has_prim_work();
-        const unsigned prim_lanes = __ballot_sync(FULL, wants_prim);
-        const unsigned starved = __ballot_sync(FULL, wants_prim && !t.has_node_work());
-        bool finished = false;
-        if (wants_prim && (starved != 0u || __popc(prim_lanes) >= tune.prim_lanes)) finished = t.prim_step(s);
-        if (t.live) {
+        // node phase
+        if (state == LANE_LIVE) {
+            if (!(ng.y & 0xFF000000u) && sp > 0) ng = stack[--sp];
+            if (ng.y & 0xFF000000u) node_step(s, ws, lane, r, ng, stack, sp);
+        }
+        __syncwarp();
+        // primitive rounds
+        uint32_t count = *(volatile uint32_t*)&ws.tail - head;
+        if (count) {
+            const bool node_work = state == LANE_LIVE && ((ng.y & 0xFF000000u) || sp > 0);
+            const unsigned node_lanes = __ballot_sync(FULL, node_work);
+            const unsigned waiting = __ballot_sync(FULL, state != LANE_IDLE && !node_work);
+            while (count >= 32u || (count > 0u && (node_lanes == 0u || __popc(waiting) >= tune.wait_lanes))) {
+                const uint32_t take = count < 32u ? count : 32u;
+                if constexpr (ANY) prim_round_any(s, ws, lane, head, take);
+                else prim_round_closest(s, ws, lane, head, take);
+                head += take;
+                count -= take;
+            }
+            r.tmax = ws.tmax32[lane];
+        }
+        // finish
+        if (state != LANE_IDLE) {
+            const uint32_t pend = ws.pend[lane];
             if constexpr (ANY) {
-                if (finished) { src.store(s, id, true); t.live = false; }
-                else if (t.advance()) { src.store(s, id, false); t.live = false; }
+                if (state == LANE_LIVE) {
+                    if (ws.best[lane]) { src.store_any(id, true); state = LANE_DRAIN; }
+                    else if (!(ng.y & 0xFF000000u) && sp == 0 && pend == 0u) { src.store_any(id, false); state = LANE_IDLE; }
+                }
+                if (state == LANE_DRAIN && pend == 0u) state = LANE_IDLE;  // its stale tests have left the queue
             } else {
-                if (t.advance()) { src.store(s, id, t); t.live = false; }
+                if (!(ng.y & 0xFF000000u) && sp == 0 && pend == 0u) {
+                    src.store_closest(s, id, ws.best[lane], ws.tmax[lane]);
+                    state = LANE_IDLE;
+                }
             }
         }
     }
@@ -215,7 +271,7 @@ __global__ void __launch_bounds__(128) k_trace_closest_exact(SceneView s, const 
     const cray_ray r = rays[i];
     Hit h;
     const bool found = traverse_exact<false>(s, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), r.max_distance, h);
-    write_hit(s, s.bin_prims, r, h, found, i, hits, surf);
+    write_hit(s, s.bin_prims, r, h, true, found, i, hits, surf);
 }
 
 __global__ void __launch_bounds__(128) k_trace_any_exact(SceneView s, const cray_ray* __restrict__ rays, uint64_t n, uint8_t* __restrict__ occluded) {
@@ -331,7 +387,7 @@ __global__ void __launch_bounds__(128) k_extend_exact(SceneView s, Pool p, const
     Hit h;
     traverse_exact<false>(s, mk(p.ox[i], p.oy[i], p.oz[i]), mk(p.dx[i], p.dy[i], p.dz[i]), inf_f64(), h);
     p.hit_slot[i] = h.slot;
-    p.hit_t[i] = h.t; p.hit_u[i] = h.u; p.hit_v[i] = h.v;
+    p.hit_t[i] = h.t;
 }
 
 // One iteration of the `while` loop of estimate_Li (path_integrator.rs:54-212) for one path.
@@ -375,7 +431,13 @@ __global__ void __launch_bounds__(128) k_shade(SceneView s, Pool p, Job job, Cou
     const LeafPrim lp = load_leaf_prim((job.exact ? s.bin_prims : s.wide_prims) + slot);
     V3 location, normal;
     double tu, tv;
-    surface_at(s, lp, ro, rd, p.hit_t[i], p.hit_u[i], p.hit_v[i], location, normal, tu, tv);
+    const double hit_t = p.hit_t[i];
+    double bu = 0.0, bv = 0.0;
+    if ((lp.kind & 0xFFu) == PRIM_TRIANGLE) {  // the barycentrics the traversal computed for this hit (same code, same bits)
+        double t2;
+        triangle_eval(lp.d, ro, rd, t2, bu, bv);
+    }
+    surface_at(s, lp, ro, rd, hit_t, bu, bv, location, normal, tu, tv);
     const cray_primitive_desc prim = s.prims[lp.prim];
     const DevMaterial& material = s.materials[prim.material];
 
@@ -500,7 +562,8 @@ struct PoolStorage {
     double* d_film = nullptr;
     uint64_t film_elems = 0;
     unsigned persistent_blocks = 0;   // SMs x resident CTAs of the persistent traversal kernel
-    WideTuning tune{8, 10};
+    WideTuning tune{8, 8};
+    unsigned shadow_blocks = 0;       // the any-hit instantiation needs fewer registers: its own occupancy
     unsigned long long* d_trace_counters = nullptr;  // {n, cursor} for the S3 entry points
 };
 
@@ -515,20 +578,22 @@ int ensure_pool(cray_scene* sc, uint32_t capacity) {
         int per_sm = 0;
         CRAY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wide_persistent<false, ExtendSource>, 128, 0));
         ps->persistent_blocks = (unsigned)(sms * std::max(per_sm, 1));
+        CRAY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wide_persistent<true, ShadowSource>, 128, 0));
+        ps->shadow_blocks = (unsigned)(sms * std::max(per_sm, 1));
         if (const char* e = std::getenv("CRAY_REFILL_LANES")) ps->tune.refill_lanes = std::max(1, std::min(32, std::atoi(e)));
-        if (const char* e = std::getenv("CRAY_PRIM_LANES")) ps->tune.prim_lanes = std::max(1, std::min(32, std::atoi(e)));
-        if (const char* e = std::getenv("CRAY_BLOCKS_PER_SM")) ps->persistent_blocks = (unsigned)(sms * std::max(1, std::atoi(e)));
+        if (const char* e = std::getenv("CRAY_WAIT_LANES")) ps->tune.wait_lanes = std::max(1, std::min(33, std::atoi(e)));
+        if (const char* e = std::getenv("CRAY_BLOCKS_PER_SM")) ps->persistent_blocks = ps->shadow_blocks = (unsigned)(sms * std::max(1, std::atoi(e)));
     }
     if (ps->pool.capacity >= capacity) return CRAY_OK;
     if (ps->slab) { cudaFree(ps->slab); ps->slab = nullptr; }
     const size_t n = capacity;
-    const size_t n_f64 = 24, n_u32 = 8;
+    const size_t n_f64 = 21, n_u32 = 8;
     const size_t bytes = n * (n_f64 * 8 + n_u32 * 4);
     CRAY_CUDA(cudaMalloc(&ps->slab, bytes));
     CRAY_CUDA(cudaMemsetAsync(ps->slab, 0, bytes, sc->stream));
     double* f = static_cast<double*>(ps->slab);
     Pool& p = ps->pool;
-    double** fields[] = {&p.ox, &p.oy, &p.oz, &p.dx, &p.dy, &p.dz, &p.hit_t, &p.hit_u, &p.hit_v, &p.beta_r, &p.beta_g, &p.beta_b,
+    double** fields[] = {&p.ox, &p.oy, &p.oz, &p.dx, &p.dy, &p.dz, &p.hit_t, &p.beta_r, &p.beta_g, &p.beta_b,
                          &p.L_r, &p.L_g, &p.L_b, &p.prev_bsdf_pdf, &p.sdx, &p.sdy, &p.sdz, &p.smax, &p.sc_r, &p.sc_g, &p.sc_b};
     size_t k = 0;
     for (double** fp : fields) { *fp = f + k * n; ++k; }
@@ -555,7 +620,7 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
     CRAY_CUDA(cudaEventCreate(&t0)); CRAY_CUDA(cudaEventCreate(&t1));
     CRAY_CUDA(cudaEventRecord(e0, stream));
     const unsigned g256 = (capacity + 255) / 256;
-    const unsigned gp = ps->persistent_blocks;
+    const unsigned gp = ps->persistent_blocks, gs = ps->shadow_blocks;
     uint64_t iterations = 0, launches = 0, closest = 0;
     double trace_ms = 0.0;
     const size_t per_iteration = sizeof(Counters) - offsetof(Counters, n_extend);
@@ -577,7 +642,7 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
         k_shade<<<g_live, 128, 0, stream>>>(sc->view, pool, job, dc);
         // at most one shadow ray per shaded vertex; the queue length lives on the device
         if (job.exact) k_shadow_exact<<<g_live, 128, 0, stream>>>(sc->view, pool, &dc->n_shadow);
-        else k_wide_persistent<true, ShadowSource><<<gp, 128, 0, stream>>>(sc->view, ShadowSource{pool}, &dc->n_shadow, &dc->shadow_cursor, ps->tune);
+        else k_wide_persistent<true, ShadowSource><<<gs, 128, 0, stream>>>(sc->view, ShadowSource{pool}, &dc->n_shadow, &dc->shadow_cursor, ps->tune);
         launches += 3;
         iterations += 1;
         if (timed) {
@@ -645,7 +710,7 @@ static int launch_trace(cray_scene* sc, int mode, bool any, const cray_ray* d_ra
         const unsigned long long init[2] = {n, 0ull};
         CRAY_CUDA(cudaMemcpyAsync(ps->d_trace_counters, init, sizeof(init), cudaMemcpyHostToDevice, stream));
         const RayArraySource src{d_rays, d_hits, d_surf, d_occluded};
-        const unsigned blocks = (unsigned)std::min<uint64_t>(ps->persistent_blocks, (n + 127) / 128);
+        const unsigned blocks = (unsigned)std::min<uint64_t>(any ? ps->shadow_blocks : ps->persistent_blocks, (n + 127) / 128);
         if (any) k_wide_persistent<true, RayArraySource><<<blocks, 128, 0, stream>>>(sc->view, src, ps->d_trace_counters, ps->d_trace_counters + 1, ps->tune);
         else k_wide_persistent<false, RayArraySource><<<blocks, 128, 0, stream>>>(sc->view, src, ps->d_trace_counters, ps->d_trace_counters + 1, ps->tune);
     }

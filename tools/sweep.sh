@@ -1,7 +1,16 @@
 #!/bin/bash
-# parameter sweep of the persistent traversal (GPU box)
-for cfg in "8 10" "4 10" "16 10" "8 4" "8 16" "8 24" "12 16" "16 20" "1 1"; do
+# parameter sweep of the persistent traversal (GPU box): library variants x refill / wait thresholds
+run() {  # label, env...
+  label=$1; shift
+  env "$@" python bench.py --spp 128 --steps 2 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('$label', round(d['value'],1), 'Mrays/s  extend_ms', round(d['roofline']['kernel_ms'],1), 'step_ms', round(d['ms_per_step'],1), 'share', round(d['roofline']['kernel_share_of_step'],3))"
+}
+for v in "" _mb5 _mb4 _mb8; do
+  run "lib=$v refill=8 wait=8" CRAY_B200_LIB=$PWD/craytracer_b200/libcray_b200$v.so
+done
+for cfg in "4 8" "16 8" "8 4" "8 16" "8 33" "12 12"; do
   set -- $cfg
-  CRAY_REFILL_LANES=$1 CRAY_PRIM_LANES=$2 python bench.py --spp 128 --steps 2 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('refill=$1 prim=$2', round(d['value'],1), 'Mrays/s extend_ms', round(d['roofline']['kernel_ms'],1), 'step_ms', round(d['ms_per_step'],1))"
+  run "lib=default refill=$1 wait=$2" CRAY_REFILL_LANES=$1 CRAY_WAIT_LANES=$2
 done
