@@ -132,6 +132,7 @@ EXTRA_SIGNATURES = {
     "cray_debug_matrix_inverse": (C.c_int, [_P, _P]),
     "cray_debug_camera_matrices": (None, [C.POINTER(CameraDesc), _P]),
     "cray_debug_check_wide_bvh": (C.c_int, [C.POINTER(SceneDesc), _P]),
+    "cray_debug_wide_stats": (C.c_int, [_P]),
     "cray_debug_tokenize": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     "cray_debug_parse_raw_value": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
 }

@@ -279,9 +279,29 @@ float float_down(double x) {
     return f;
 }
 
+// ---- cost-optimal collapse (dynamic programme over the binary tree) ----------------------------------------------------
+//
+// Every primitive ends up alone in some leaf slot with its own box, so the SAH cost of the primitive tests is the same for
+// every collapse; what varies is the sum over wide nodes of their surface area (the chance that a ray has to test the
+// node's 8 child boxes).  With C(n, i) = the least such sum when the subtree of binary node n hangs off its parent as at
+// most i children (Ylitie, Karras, Laine 2017, sec. 3.2):
+//   D(n, j) = min over 0 < k < j of  C(left, k) + C(right, j - k)          j = 2..8
+//   C(n, 1) = area(n) + D(n, 8)                                            n becomes a wide node
+//   C(n, i) = min(D(n, i), C(n, i - 1))                                    i = 2..7
+//   C(primitive, i) = 0
+// Leaves of the reference tree with 2..4 primitives take part as small binary subtrees over their primitives.
+constexpr uint32_t kPrimRef = 0x80000000u;
+
+struct DpNode {
+    uint32_t left, right;   // index into the DP array, or kPrimRef | primitive
+    float area;
+    float cost[7];          // C(n, 1..7)
+    uint8_t split[7];       // for j = 2..8: k of D(n, j) in the low 3 bits; bit 7 (j <= 7): C(n, j) falls back to C(n, j - 1)
+    uint8_t _pad;
+};
+
 struct Kid {
-    uint32_t id;     // is_prim: primitive index; else binary node index
-    bool is_prim;
+    uint32_t ref;    // kPrimRef | primitive, or DP node index
     Box3 box;
 };
 
@@ -290,20 +310,97 @@ struct Collapser {
     const RefBvh& ref;
     WideBvh& out;
     uint32_t max_depth = 0;
+    std::vector<DpNode> dp;          // [0, ref.nodes.size()): the reference nodes; then the virtual nodes inside multi-primitive leaves
+    std::vector<Box3> virtual_box;   // boxes of the virtual nodes
 
-    Kid node_kid(uint32_t bin) const {
-        const BinNode& n = ref.nodes[bin];
-        if (n.axis == 3 && n.b == 1) {  // a one-primitive leaf is just that primitive
-            const uint32_t prim = ref.prim_order[n.a];
-            return {prim, true, primitive_bounds(desc, prim)};
-        }
-        return {bin, false, n.box};
+    Box3 box_of(uint32_t r) const {
+        if (r & kPrimRef) return primitive_bounds(desc, r & ~kPrimRef);
+        return r < ref.nodes.size() ? ref.nodes[r].box : virtual_box[r - ref.nodes.size()];
     }
-    // how many slots opening this kid adds
-    int growth(const Kid& k) const {
-        if (k.is_prim) return -1;  // cannot be opened
-        const BinNode& n = ref.nodes[k.id];
-        return n.axis == 3 ? (int)n.b - 1 : 1;
+    float cost_of(uint32_t r, int i) const { return (r & kPrimRef) ? 0.0f : dp[r].cost[i - 1]; }
+
+    void solve(DpNode& n) {
+        float d[9];
+        uint8_t dk[9];
+        for (int j = 2; j <= 8; ++j) {
+            float best = HUGE_VALF;
+            int bk = 1;
+            for (int k = 1; k < j; ++k) {
+                if (k > 7 || j - k > 7) continue;
+                const float c = cost_of(n.left, k) + cost_of(n.right, j - k);
+                if (c < best) { best = c; bk = k; }
+            }
+            d[j] = best;
+            dk[j] = (uint8_t)bk;
+        }
+        n.cost[0] = n.area + d[8];
+        n.split[6] = dk[8];
+        for (int i = 2; i <= 7; ++i) {
+            if (d[i] <= n.cost[i - 2]) { n.cost[i - 1] = d[i]; n.split[i - 2] = dk[i]; }
+            else { n.cost[i - 1] = n.cost[i - 2]; n.split[i - 2] = (uint8_t)(dk[i] | 0x80u); }
+        }
+    }
+
+    uint32_t ref_of_child(uint32_t bin) const {
+        const BinNode& c = ref.nodes[bin];
+        return (c.axis == 3 && c.b == 1) ? (kPrimRef | ref.prim_order[c.a]) : bin;
+    }
+    uint32_t add_virtual(uint32_t l, uint32_t r) {
+        DpNode v{};
+        v.left = l; v.right = r;
+        const Box3 b = box_union(box_of(l), box_of(r));
+        v.area = (float)box_surface_area(b);
+        virtual_box.push_back(b);
+        solve(v);
+        dp.push_back(v);
+        return (uint32_t)dp.size() - 1;
+    }
+
+    void run_dp() {
+        const size_t nr = ref.nodes.size();
+        dp.assign(nr, DpNode{});
+        // children follow their parents in the pre-order array: a reverse sweep sees them first
+        for (size_t i = nr; i-- > 0;) {
+            const BinNode& b = ref.nodes[i];
+            DpNode n{};
+            n.area = (float)box_surface_area(b.box);
+            if (b.axis == 3) {
+                if (b.b == 1) continue;  // referenced as a primitive, never as a node
+                uint32_t p[4];
+                for (uint32_t k = 0; k < b.b; ++k) p[k] = kPrimRef | ref.prim_order[b.a + k];
+                if (b.b == 2) { n.left = p[0]; n.right = p[1]; }
+                else if (b.b == 3) { n.left = add_virtual(p[0], p[1]); n.right = p[2]; }
+                else { n.left = add_virtual(p[0], p[1]); n.right = add_virtual(p[2], p[3]); }
+            } else {
+                n.left = ref_of_child(b.a);
+                n.right = ref_of_child(b.b);
+            }
+            solve(n);
+            dp[i] = n;
+        }
+    }
+
+    // The children subtree r contributes when it may use at most i slots of its parent.
+    void collect(uint32_t r, int i, std::vector<Kid>& kids) const {
+        if (r & kPrimRef) { kids.push_back({r, box_of(r)}); return; }
+        const DpNode& n = dp[r];
+        while (i >= 2 && (n.split[i - 2] & 0x80u)) i -= 1;
+        if (i == 1) { kids.push_back({r, box_of(r)}); return; }
+        const int k = n.split[i - 2] & 7;
+        collect(n.left, k, kids);
+        collect(n.right, i - k, kids);
+    }
+
+    void expand(uint32_t wide_idx, uint32_t r, uint32_t depth) {
+        std::vector<Kid> kids;
+        if (r & kPrimRef) kids.push_back({r, box_of(r)});  // a scene of one primitive
+        else {
+            const DpNode& n = dp[r];
+            const int k = n.split[6] & 7;
+            collect(n.left, k, kids);
+            collect(n.right, 8 - k, kids);
+        }
+        emit(wide_idx, kids, box_of(r), depth);
     }
 
     void emit(uint32_t wide_idx, const std::vector<Kid>& kids, const Box3& node_box, uint32_t depth) {
@@ -350,7 +447,7 @@ struct Collapser {
         }
         w.ex = (uint8_t)(e[0] + 127); w.ey = (uint8_t)(e[1] + 127); w.ez = (uint8_t)(e[2] + 127);
         w.prim_base = (uint32_t)out.prim_order.size();
-        std::vector<Kid> interior_kids;
+        std::vector<uint32_t> interior_kids;
         for (int s = 0; s < 8; ++s) {
             const int c = child_in[s];
             if (c < 0) continue;
@@ -365,59 +462,19 @@ struct Collapser {
                 w.qlo[ax][s] = (uint8_t)ql;
                 w.qhi[ax][s] = (uint8_t)qh;
             }
-            if (kid.is_prim) {
+            if (kid.ref & kPrimRef) {
                 w.leafmask |= (uint8_t)(1u << s);
-                out.prim_order.push_back(kid.id);
+                out.prim_order.push_back(kid.ref & ~kPrimRef);
             } else {
                 w.imask |= (uint8_t)(1u << s);
-                interior_kids.push_back(kid);
+                interior_kids.push_back(kid.ref);
             }
         }
         w.child_base = (uint32_t)out.nodes.size();
         out.nodes[wide_idx] = w;
         const uint32_t base = (uint32_t)out.nodes.size();
         out.nodes.resize(out.nodes.size() + interior_kids.size());
-        for (size_t i = 0; i < interior_kids.size(); ++i) expand(base + (uint32_t)i, interior_kids[i].id, depth + 1);
-    }
-
-    // Open the binary subtree rooted at `bin` into up to 8 children, largest surface area first.  Opening an
-    // interior node adds one child; opening a leaf of n primitives adds n - 1 (each primitive gets its own slot).
-    void expand(uint32_t wide_idx, uint32_t bin, uint32_t depth) {
-        std::vector<Kid> kids;
-        const BinNode& root = ref.nodes[bin];
-        if (root.axis == 3) {
-            for (uint32_t i = 0; i < root.b; ++i) {
-                const uint32_t prim = ref.prim_order[root.a + i];
-                kids.push_back({prim, true, primitive_bounds(desc, prim)});
-            }
-        } else {
-            kids.push_back(node_kid(root.a));
-            kids.push_back(node_kid(root.b));
-        }
-        for (;;) {
-            int pick = -1;
-            double best = -1.0;
-            for (size_t i = 0; i < kids.size(); ++i) {
-                const int g = growth(kids[i]);
-                if (g < 0 || kids.size() + (size_t)g > 8) continue;
-                const double sa = box_surface_area(kids[i].box);
-                if (sa > best) { best = sa; pick = (int)i; }
-            }
-            if (pick < 0) break;
-            const BinNode c = ref.nodes[kids[pick].id];
-            if (c.axis == 3) {
-                const uint32_t first = ref.prim_order[c.a];
-                kids[pick] = {first, true, primitive_bounds(desc, first)};
-                for (uint32_t i = 1; i < c.b; ++i) {
-                    const uint32_t prim = ref.prim_order[c.a + i];
-                    kids.push_back({prim, true, primitive_bounds(desc, prim)});
-                }
-            } else {
-                kids[pick] = node_kid(c.a);
-                kids.push_back(node_kid(c.b));
-            }
-        }
-        emit(wide_idx, kids, root.box, depth);
+        for (size_t i = 0; i < interior_kids.size(); ++i) expand(base + (uint32_t)i, interior_kids[i], depth + 1);
     }
 };
 
@@ -425,11 +482,12 @@ struct Collapser {
 
 void collapse_to_wide(const cray_scene_desc& d, const RefBvh& ref, WideBvh& out) {
     out = WideBvh{};
-    out.nodes.reserve(ref.nodes.size() / 4 + 16);
+    out.nodes.reserve(ref.prim_order.size() / 5 + 16);
     out.prim_order.reserve(ref.prim_order.size());
     out.nodes.resize(1);
     Collapser c{d, ref, out};
-    c.expand(0, 0, 1);
+    c.run_dp();
+    c.expand(0, c.ref_of_child(0), 1);
     out.depth = c.max_depth;
 }
 

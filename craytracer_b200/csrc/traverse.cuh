@@ -222,7 +222,8 @@ __device__ __forceinline__ void node_step(const SceneView& s, WarpShared& ws, un
         do {
             const uint32_t k = __ffs(lh) - 1u;
             lh &= lh - 1u;
-            ws.queue[pos & (kQueue - 1u)] = tag | (prim_base + __popc(leafmask & ((1u << k) - 1u)));
+            const uint32_t leaf_slot = prim_base + __popc(leafmask & ((1u << k) - 1u));
+            ws.queue[pos & (kQueue - 1u)] = tag | leaf_slot;
             pos += 1u;
         } while (lh);
     }
@@ -251,39 +252,36 @@ __device__ __forceinline__ void prim_round_closest(const SceneView& s, WarpShare
         t = verdict == 1 ? cand : rmax;
         my_prim = lp.prim;
     }
+    // accepted distances are positive f64: they order like their bit patterns, so one shared-memory atomicMin per
+    // accepting lane leaves the ray's new closest distance in ws.tmax (a verdict-2 lane's t IS the current value)
+    if (verdict == 1) atomicMin(reinterpret_cast<unsigned long long*>(&ws.tmax[owner]), (unsigned long long)__double_as_longlong(t));
+    __syncwarp();
     const unsigned grp = __match_any_sync(FULL, act ? owner : 32u + lane);
-    // accepted distances are positive f64: they order like their bit patterns
-    const uint32_t hi = verdict ? (uint32_t)__double2hiint(t) : 0x7FFFFFFFu;
-    const uint32_t hmin = __reduce_min_sync(grp, hi);
-    const uint32_t lo = (verdict && hi == hmin) ? (uint32_t)__double2loint(t) : 0xFFFFFFFFu;
-    const uint32_t lmin = __reduce_min_sync(grp, lo);
-    const bool win = verdict && hi == hmin && (uint32_t)__double2loint(t) == lmin;
+    const bool win = verdict != 0 && ws.tmax[owner] == t;
     const unsigned wins = __ballot_sync(FULL, win) & grp;
+    // exact-t ties: several winners in this round, or (verdict 2) a winner level with the best of an earlier round
     const bool tie = win && (__popc(wins) > 1 || verdict == 2);
     if (win && !tie) {
-        ws.tmax[owner] = t;
         ws.tmax32[owner] = slab_tmax(t);
         ws.best[owner] = slot;
     }
     if (act && lane == (unsigned)(__ffs(grp) - 1)) ws.pend[owner] -= __popc(grp);
     unsigned ties = __ballot_sync(FULL, tie);
-    while (ties) {
-        __syncwarp();
+    while (ties) {  // rare: one tied lane at a time, in lane order
         const unsigned l = __ffs(ties) - 1u;
         ties &= ties - 1u;
         if (lane == l) {
-            const uint32_t cur = ws.best[owner];
-            const double cur_t = ws.tmax[owner];
-            bool take = false;
-            if (cur == CRAY_NO_HIT || t < cur_t) take = true;
-            else if (t == cur_t && cur != slot)
-                take = reference_visits_first(s, s.rank_of_prim[my_prim], s.rank_of_prim[s.wide_prims[cur].prim], dir);
-            if (take) {
-                ws.tmax[owner] = t;
-                ws.tmax32[owner] = slab_tmax(t);
-                ws.best[owner] = slot;
+            // the first verdict-1 winner of a group displaces the (farther) previous best; everyone else is compared with
+            // the primitive currently holding this distance
+            bool take = verdict == 1 && lane == (unsigned)(__ffs(wins) - 1);
+            if (!take) {
+                const uint32_t cur = ws.best[owner];
+                take = cur != slot && reference_visits_first(s, s.rank_of_prim[my_prim], s.rank_of_prim[s.wide_prims[cur].prim], dir);
             }
+            if (take) ws.best[owner] = slot;
+            ws.tmax32[owner] = slab_tmax(t);
         }
+        __syncwarp();
     }
     __syncwarp();
 }

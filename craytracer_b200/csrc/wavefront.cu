@@ -178,6 +178,19 @@ constexpr int kWideMinBlocks = CRAY_WIDE_MIN_BLOCKS;   // CTAs of 128 threads pe
 
 enum : int { LANE_IDLE = 0, LANE_LIVE = 1, LANE_DRAIN = 2 };
 
+// Tuning build (make VARIANT=stats EXTRA=-DCRAY_WIDE_STATS=1): work counters of the traversal kernels, read with
+// cray_debug_wide_stats.  [0] rays  [1] warp iterations  [2] node steps (lanes)  [3] node phases (warps)
+// [4] primitive tests (lanes)  [5] primitive rounds (warps)  [6] refills (warps)  [7] idle-lane iterations
+#ifndef CRAY_WIDE_STATS
+#define CRAY_WIDE_STATS 0
+#endif
+#if CRAY_WIDE_STATS
+__device__ unsigned long long g_wide_stats[2][8];
+#define WIDE_STAT(k, v) stat[k] += (unsigned long long)(v)
+#else
+#define WIDE_STAT(k, v)
+#endif
+
 template <bool ANY, class Source>
 __global__ void __launch_bounds__(128, kWideMinBlocks) k_wide_persistent(SceneView s, Source src, const unsigned long long* __restrict__ n_ptr, unsigned long long* cursor, WideTuning tune) {
     __shared__ WarpShared shared[4];
@@ -189,6 +202,9 @@ __global__ void __launch_bounds__(128, kWideMinBlocks) k_wide_persistent(SceneVi
     ws.pend[lane] = 0u;
     __syncwarp();
     uint32_t head = 0;  // queue entries consumed so far (warp-uniform)
+#if CRAY_WIDE_STATS
+    unsigned long long stat[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     WideRay r;
     uint2 ng = make_uint2(0u, 0u);
     uint2 stack[kWideStack];
@@ -198,8 +214,11 @@ __global__ void __launch_bounds__(128, kWideMinBlocks) k_wide_persistent(SceneVi
     bool exhausted = false;
     for (;;) {
         const unsigned idle = __ballot_sync(FULL, state == LANE_IDLE);
+        WIDE_STAT(1, 1);
+        WIDE_STAT(7, __popc(idle));  // counters are warp-uniform; lane 0 publishes them
         if (!exhausted && (idle == FULL || __popc(idle) >= tune.refill_lanes)) {
             const int want = __popc(idle);
+            WIDE_STAT(6, 1);
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(cursor, (unsigned long long)want);
             base = __shfl_sync(FULL, base, 0);
@@ -216,6 +235,7 @@ __global__ void __launch_bounds__(128, kWideMinBlocks) k_wide_persistent(SceneVi
                     state = LANE_LIVE;
                 }
             }
+            WIDE_STAT(0, __popc(__ballot_sync(FULL, state == LANE_LIVE) & idle));
             if (base + want >= n) exhausted = true;
         }
         if (__ballot_sync(FULL, state != LANE_IDLE) == 0u) {
@@ -223,10 +243,19 @@ __global__ void __launch_bounds__(128, kWideMinBlocks) k_wide_persistent(SceneVi
             continue;
         }
         // node phase
+        bool stepping = false;
         if (state == LANE_LIVE) {
             if (!(ng.y & 0xFF000000u) && sp > 0) ng = stack[--sp];
-            if (ng.y & 0xFF000000u) node_step(s, ws, lane, r, ng, stack, sp);
+            stepping = (ng.y & 0xFF000000u) != 0u;
+            if (stepping) node_step(s, ws, lane, r, ng, stack, sp);
         }
+#if CRAY_WIDE_STATS
+        {
+            const unsigned m = __ballot_sync(FULL, stepping);
+            WIDE_STAT(2, __popc(m));
+            WIDE_STAT(3, m != 0u);
+        }
+#endif
         __syncwarp();
         // primitive rounds
         uint32_t count = *(volatile uint32_t*)&ws.tail - head;
@@ -240,6 +269,8 @@ __global__ void __launch_bounds__(128, kWideMinBlocks) k_wide_persistent(SceneVi
                 else prim_round_closest(s, ws, lane, head, take);
                 head += take;
                 count -= take;
+                WIDE_STAT(4, take);
+                WIDE_STAT(5, 1);
             }
             r.tmax = ws.tmax32[lane];
         }
@@ -260,6 +291,10 @@ __global__ void __launch_bounds__(128, kWideMinBlocks) k_wide_persistent(SceneVi
             }
         }
     }
+#if CRAY_WIDE_STATS
+    if (lane == 0)
+        for (int k = 0; k < 8; ++k) atomicAdd(&g_wide_stats[ANY ? 1 : 0][k], stat[k]);
+#endif
 }
 
 // ---- exact-mode kernels (reference binary BVH, one thread per ray) ------------------------------------------------------
@@ -391,7 +426,10 @@ __global__ void __launch_bounds__(128) k_extend_exact(SceneView s, Pool p, const
 }
 
 // One iteration of the `while` loop of estimate_Li (path_integrator.rs:54-212) for one path.
-__global__ void __launch_bounds__(128) k_shade(SceneView s, Pool p, Job job, Counters* counters) {
+#ifndef CRAY_SHADE_MIN_BLOCKS
+#define CRAY_SHADE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, CRAY_SHADE_MIN_BLOCKS) k_shade(SceneView s, Pool p, Job job, Counters* counters) {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= counters->n_extend) return;
     const uint32_t i = p.extend_queue[q];
@@ -683,6 +721,21 @@ int check_mode(const cray_scene* sc, int mode) {
 using namespace cray;
 
 extern "C" {
+
+// Tuning builds only (CRAY_WIDE_STATS): copies and clears the traversal work counters, [0..7] closest-hit, [8..15] any-hit.
+int cray_debug_wide_stats(unsigned long long* out16) {
+#if CRAY_WIDE_STATS
+    unsigned long long zero[16] = {};
+    CRAY_CUDA(cudaDeviceSynchronize());
+    CRAY_CUDA(cudaMemcpyFromSymbol(out16, g_wide_stats, sizeof(zero)));
+    CRAY_CUDA(cudaMemcpyToSymbol(g_wide_stats, zero, sizeof(zero)));
+    return CRAY_OK;
+#else
+    (void)out16;
+    set_error("built without CRAY_WIDE_STATS");
+    return CRAY_E_UNSUPPORTED;
+#endif
+}
 
 void cray_pool_release(cray_scene* sc) {
     auto* ps = static_cast<PoolStorage*>(sc->pool);

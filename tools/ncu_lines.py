@@ -3,6 +3,7 @@
 average number of active threads per instruction.  usage: ncu_lines.py report.ncu-rep [kernel-regex] [top]"""
 import csv
 import io
+import re
 import subprocess
 import sys
 
@@ -11,8 +12,8 @@ def main():
     rep = sys.argv[1]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
     cmd = ["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"]
-    if len(sys.argv) > 2 and sys.argv[2]:
-        cmd += ["-k", "regex:" + sys.argv[2]]
+    pattern = re.compile(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2] else None
+    selected = True
     out = subprocess.run(cmd, capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     cur_file, hdr, lines = None, None, {}
@@ -24,6 +25,9 @@ def main():
             cur_file = r[1].split("/")[-1]
             continue
         if r[0] == "Function Name":
+            selected = pattern is None or bool(pattern.search(r[1]))
+            continue
+        if not selected:
             continue
         if r[0] == "Line No":
             hdr = r
