@@ -223,6 +223,15 @@ class Scene:
         _check(_abi.lib().cray_render(self._h, mode, seed, sample_begin, sample_end, film.ctypes.data, C.byref(stats)))
         return film, stats
 
+    def render_into(self, film, seed=0, sample_begin=0, sample_end=None, mode=TRAVERSE_FAST):
+        """render() into a caller-owned host array of W*H*3 f32 (e.g. pinned memory); returns the statistics."""
+        if sample_end is None:
+            sample_end = self.num_samples
+        assert film.dtype == np.float32 and film.size == self.height * self.width * 3 and film.flags["C_CONTIGUOUS"]
+        stats = RenderStats()
+        _check(_abi.lib().cray_render(self._h, mode, seed, sample_begin, sample_end, film.ctypes.data, C.byref(stats)))
+        return stats
+
     def render_device(self, d_film, seed=0, sample_begin=0, sample_end=None, mode=TRAVERSE_FAST, stream=0):
         """Same, into a device buffer of W*H*3 f32 (e.g. a torch CUDA tensor's data_ptr())."""
         if sample_end is None:

@@ -599,10 +599,12 @@ struct PoolStorage {
     Counters* h_counters = nullptr;  // pinned
     double* d_film = nullptr;
     uint64_t film_elems = 0;
+    float* d_film_f32 = nullptr;      // staging of cray_render's host film
     unsigned persistent_blocks = 0;   // SMs x resident CTAs of the persistent traversal kernel
     WideTuning tune{8, 8};
     unsigned shadow_blocks = 0;       // the any-hit instantiation needs fewer registers: its own occupancy
     unsigned long long* d_trace_counters = nullptr;  // {n, cursor} for the S3 entry points
+    std::vector<cudaEvent_t> timers;                 // (start, stop) of every extend launch of one render, reused across calls
 };
 
 int ensure_pool(cray_scene* sc, uint32_t capacity) {
@@ -653,42 +655,44 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
     Counters* dc = ps->d_counters;
     CRAY_CUDA(cudaMemsetAsync(pool.state, 0, sizeof(uint32_t) * capacity, stream));
     CRAY_CUDA(cudaMemsetAsync(dc, 0, sizeof(Counters), stream));
-    cudaEvent_t e0, e1, t0, t1;
+    cudaEvent_t e0, e1, gen_done;
     CRAY_CUDA(cudaEventCreate(&e0)); CRAY_CUDA(cudaEventCreate(&e1));
-    CRAY_CUDA(cudaEventCreate(&t0)); CRAY_CUDA(cudaEventCreate(&t1));
+    CRAY_CUDA(cudaEventCreateWithFlags(&gen_done, cudaEventDisableTiming));
     CRAY_CUDA(cudaEventRecord(e0, stream));
-    const unsigned g256 = (capacity + 255) / 256;
+    const unsigned g256 = (capacity + 255) / 256, g128 = (capacity + 127) / 128;
     const unsigned gp = ps->persistent_blocks, gs = ps->shadow_blocks;
     uint64_t iterations = 0, launches = 0, closest = 0;
-    double trace_ms = 0.0;
     const size_t per_iteration = sizeof(Counters) - offsetof(Counters, n_extend);
-    for (;;) {
+    const bool timed = stats != nullptr;
+    // The host never waits for traversal or shading: it enqueues the whole iteration, then waits only for the iteration's
+    // k_generate (long finished by the time the GPU works through extend / shade / shadow) to learn whether any path is
+    // still alive.  The three launches behind the last, empty generate find empty queues and return at once.
+    for (size_t iter = 0;; ++iter) {
         CRAY_CUDA(cudaMemsetAsync(&dc->n_extend, 0, per_iteration, stream));
         k_generate<<<g256, 256, 0, stream>>>(sc->view, pool, job, dc);
         CRAY_CUDA(cudaMemcpyAsync(ps->h_counters, dc, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-        CRAY_CUDA(cudaStreamSynchronize(stream));
-        launches += 1;
+        CRAY_CUDA(cudaEventRecord(gen_done, stream));
+        if (timed) {
+            while (ps->timers.size() < 2 * (iter + 1)) {
+                cudaEvent_t ev;
+                CRAY_CUDA(cudaEventCreate(&ev));
+                ps->timers.push_back(ev);
+            }
+            CRAY_CUDA(cudaEventRecord(ps->timers[2 * iter], stream));
+        }
+        if (job.exact) k_extend_exact<<<g128, 128, 0, stream>>>(sc->view, pool, &dc->n_extend);
+        else k_wide_persistent<false, ExtendSource><<<gp, 128, 0, stream>>>(sc->view, ExtendSource{pool}, &dc->n_extend, &dc->extend_cursor, ps->tune);
+        if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[2 * iter + 1], stream));
+        k_shade<<<g128, 128, 0, stream>>>(sc->view, pool, job, dc);
+        // at most one shadow ray per shaded vertex; the queue length lives on the device
+        if (job.exact) k_shadow_exact<<<g128, 128, 0, stream>>>(sc->view, pool, &dc->n_shadow);
+        else k_wide_persistent<true, ShadowSource><<<gs, 128, 0, stream>>>(sc->view, ShadowSource{pool}, &dc->n_shadow, &dc->shadow_cursor, ps->tune);
+        launches += 4;
+        CRAY_CUDA(cudaEventSynchronize(gen_done));
         const uint64_t live = ps->h_counters->n_extend;
         if (live == 0) break;
         closest += live;
-        const unsigned g_live = (unsigned)((live + 127) / 128);
-        const bool timed = stats != nullptr;
-        if (timed) CRAY_CUDA(cudaEventRecord(t0, stream));
-        if (job.exact) k_extend_exact<<<g_live, 128, 0, stream>>>(sc->view, pool, &dc->n_extend);
-        else k_wide_persistent<false, ExtendSource><<<gp, 128, 0, stream>>>(sc->view, ExtendSource{pool}, &dc->n_extend, &dc->extend_cursor, ps->tune);
-        if (timed) CRAY_CUDA(cudaEventRecord(t1, stream));
-        k_shade<<<g_live, 128, 0, stream>>>(sc->view, pool, job, dc);
-        // at most one shadow ray per shaded vertex; the queue length lives on the device
-        if (job.exact) k_shadow_exact<<<g_live, 128, 0, stream>>>(sc->view, pool, &dc->n_shadow);
-        else k_wide_persistent<true, ShadowSource><<<gs, 128, 0, stream>>>(sc->view, ShadowSource{pool}, &dc->n_shadow, &dc->shadow_cursor, ps->tune);
-        launches += 3;
         iterations += 1;
-        if (timed) {
-            CRAY_CUDA(cudaEventSynchronize(t1));
-            float ms = 0;
-            CRAY_CUDA(cudaEventElapsedTime(&ms, t0, t1));
-            trace_ms += ms;
-        }
     }
     CRAY_CUDA(cudaEventRecord(e1, stream));
     CRAY_CUDA(cudaEventSynchronize(e1));
@@ -696,6 +700,12 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
     float ms = 0;
     CRAY_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     if (stats) {
+        double trace_ms = 0.0;
+        for (size_t i = 0; i < iterations; ++i) {
+            float t = 0;
+            CRAY_CUDA(cudaEventElapsedTime(&t, ps->timers[2 * i], ps->timers[2 * i + 1]));
+            trace_ms += t;
+        }
         stats->samples = job.n_total;
         stats->closest_rays = closest;
         stats->shadow_rays = ps->h_counters->shadow_rays;
@@ -705,7 +715,7 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
         stats->render_ms = ms;
         stats->trace_ms = trace_ms;
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(t0); cudaEventDestroy(t1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(gen_done);
     return CRAY_OK;
 }
 
@@ -744,7 +754,9 @@ void cray_pool_release(cray_scene* sc) {
     if (ps->d_counters) cudaFree(ps->d_counters);
     if (ps->h_counters) cudaFreeHost(ps->h_counters);
     if (ps->d_film) cudaFree(ps->d_film);
+    if (ps->d_film_f32) cudaFree(ps->d_film_f32);
     if (ps->d_trace_counters) cudaFree(ps->d_trace_counters);
+    for (cudaEvent_t ev : ps->timers) cudaEventDestroy(ev);
     delete ps;
     sc->pool = nullptr;
 }
@@ -878,6 +890,7 @@ int cray_render_device(cray_scene* sc, int mode, uint64_t seed, uint32_t sample_
     auto* ps = static_cast<PoolStorage*>(sc->pool);
     if (ps->film_elems < n_pixels * 3) {
         if (ps->d_film) cudaFree(ps->d_film);
+    if (ps->d_film_f32) cudaFree(ps->d_film_f32);
         CRAY_CUDA(cudaMalloc(&ps->d_film, n_pixels * 3 * sizeof(double)));
         ps->film_elems = n_pixels * 3;
     }
@@ -907,14 +920,15 @@ int cray_render(cray_scene* sc, int mode, uint64_t seed, uint32_t sample_begin, 
     if (!sc || !rgb_sum) { set_error("bad arguments"); return CRAY_E_INVALID; }
     CRAY_CUDA(cudaSetDevice(sc->device));
     const uint64_t n = (uint64_t)sc->info.width * sc->info.height * 3;
-    float* d_out = nullptr;
-    CRAY_CUDA(cudaMalloc(&d_out, n * sizeof(float)));
-    int rc = cray_render_device(sc, mode, seed, sample_begin, sample_end, d_out, sc->stream, stats);
-    cudaError_t e = cudaSuccess;
-    if (rc == CRAY_OK) e = cudaMemcpy(rgb_sum, d_out, n * sizeof(float), cudaMemcpyDeviceToHost);
-    cudaFree(d_out);
-    if (e != cudaSuccess) return cuda_fail(e, "cray_render");
-    return rc;
+    int rc = ensure_pool(sc, 1);
+    if (rc != CRAY_OK) return rc;
+    auto* ps = static_cast<PoolStorage*>(sc->pool);
+    if (!ps->d_film_f32) CRAY_CUDA(cudaMalloc(&ps->d_film_f32, n * sizeof(float)));  // film size is fixed per scene
+    rc = cray_render_device(sc, mode, seed, sample_begin, sample_end, ps->d_film_f32, sc->stream, stats);
+    if (rc != CRAY_OK) return rc;
+    CRAY_CUDA(cudaMemcpyAsync(rgb_sum, ps->d_film_f32, n * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
+    CRAY_CUDA(cudaStreamSynchronize(sc->stream));
+    return CRAY_OK;
 }
 
 }  // extern "C"
