@@ -208,7 +208,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        totals = {"closest": 0, "shadow": 0, "launches": 0, "trace_ms": 0.0, "render_ms": 0.0, "iters": 0, "nan": 0}
+        totals = {"closest": 0, "shadow": 0, "launches": 0, "trace_ms": 0.0, "render_ms": 0.0, "iters": 0, "nan": 0, "shade_ms": 0.0, "shadow_ms": 0.0,
+                  "generate_ms": 0.0}
         start.record(stream)
         for k in range(args.steps):
             st = step(k, e2e)
@@ -216,6 +217,9 @@ def run_ours(args):
             totals["shadow"] += st.shadow_rays
             totals["launches"] += st.kernel_launches + (1 if rank == 0 else 0)
             totals["trace_ms"] += st.trace_ms
+            totals["shade_ms"] += st.shade_ms
+            totals["shadow_ms"] += st.shadow_ms
+            totals["generate_ms"] += st.generate_ms
             totals["render_ms"] += st.render_ms
             totals["iters"] += st.iterations
             totals["nan"] += st.nan_samples
@@ -267,6 +271,8 @@ def run_ours(args):
                          "frac": achieved / peak, "peak_source": peak_kind, "algorithmic_bytes_per_ray": ALGORITHMIC_BYTES_PER_RAY,
                          "rays_in_kernel": totals["closest"], "kernel_ms": extend_ms, "kernel_share_of_step": extend_ms / max(totals["render_ms"], 1e-9),
                          "traffic": traffic},
+            "stage_ms_per_step": {"extend": totals["trace_ms"] / args.steps, "shade": totals["shade_ms"] / args.steps, "shadow": totals["shadow_ms"] / args.steps,
+                                  "generate": totals["generate_ms"] / args.steps, "iterations": totals["iters"] / args.steps},
             "clocks": clocks,
             "setup": {"parse_and_standin_s": parse_s, "bvh_build_ms": scene.info.bvh_build_ms, "upload_ms": scene.info.upload_ms, "scene_create_s": create_s,
                       "wide_nodes": scene.info.wide_nodes, "wide_depth": scene.info.wide_depth, "triangles": hs.desc.n_triangles},

@@ -75,7 +75,8 @@ class SceneDesc(C.Structure):
 
 class RenderStats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("nan_samples", C.c_uint64),
-                ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("render_ms", C.c_double), ("trace_ms", C.c_double)]
+                ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("render_ms", C.c_double), ("trace_ms", C.c_double),
+                ("shadow_ms", C.c_double), ("shade_ms", C.c_double), ("generate_ms", C.c_double)]
 
 
 class SceneInfo(C.Structure):

@@ -7,6 +7,10 @@
 #pragma once
 #include "cray_math.cuh"
 
+#ifndef CRAY_SOBOL_BYTES
+#define CRAY_SOBOL_BYTES 1
+#endif
+
 namespace cray {
 
 // ---- SipHash-1-3, k0 = k1 = 0, over (seed, x, y) as three little-endian u64 words (sampling.rs:223-228) ----
@@ -68,13 +72,20 @@ CRAY_HD uint32_t owen_scramble_rev(uint32_t n_rev, uint32_t scramble) {
     n_rev ^= n_rev * 0x53a22864u;
     return n_rev;
 }
-// `directions` = SOBOL_DIRECTIONS[256][32]; only the first 16 vectors of a dimension are used (2^16 indices).
-CRAY_HD float sobol_sample(const uint32_t* directions, uint32_t shuffled_rev_index, uint32_t dimension, uint32_t seed) {
-    const uint32_t* vecs = directions + 32u * (dimension & 255u);
+// `table` = the Joe-Kuo direction vectors folded into byte tables, [256 dimensions][2][256] (scene_device.cu): entry
+// [d][h][b] is the XOR of the vectors k = 8h .. 8h+7 of dimension d whose index bit (0x80 >> (k - 8h)) is set in b.  Only the
+// top 16 bits of the reversed index are used (2^16 indices), so a sample is two table reads instead of sixteen.
+__device__ __forceinline__ float sobol_sample(const uint32_t* __restrict__ table, uint32_t shuffled_rev_index, uint32_t dimension, uint32_t seed) {
+#if CRAY_SOBOL_BYTES
+    const uint32_t* t = table + 512u * (dimension & 255u);
+    const uint32_t sobol = __ldg(t + (shuffled_rev_index >> 24)) ^ __ldg(t + 256u + ((shuffled_rev_index >> 16) & 255u));
+#else  // tuning build: the plain direction vectors, [256][32]
+    const uint32_t* vecs = table + 32u * (dimension & 255u);
     uint32_t sobol = 0;
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         if (shuffled_rev_index & (0x80000000u >> k)) sobol ^= vecs[k];
+#endif
     const uint32_t dim_seed = seed ^ (dimension * 0x9e3779b9u + 0x7f4a7c15u);
     const uint32_t scrambled = reverse_bits32(owen_scramble_rev(reverse_bits32(sobol), dim_seed));
     return (float)(scrambled >> 8) * (1.0f / 16777216.0f);
@@ -84,16 +95,26 @@ struct PixelSampler {  // SobolSampler, sampling.rs:197-247
     uint32_t hash;           // per-pixel scramble seed
     uint32_t shuffled_rev;   // Owen-shuffled, bit-reversed sample index (depends on hash and sample_index only)
     uint32_t dimension;
-    CRAY_HD void start_pixel(uint64_t seed, uint32_t x, uint32_t y, uint32_t sample_index) {
+    __device__ __forceinline__ void start_pixel(uint64_t seed, uint32_t x, uint32_t y, uint32_t sample_index) {
         hash = pixel_hash(seed, x, y);
         shuffled_rev = owen_scramble_rev(reverse_bits32(sample_index), hash);
         dimension = 0;
     }
-    CRAY_HD double sample_1d(const uint32_t* directions) {
-        const float v = sobol_sample(directions, shuffled_rev, dimension, hash);
+    __device__ __forceinline__ double sample_1d(const uint32_t* table) {
+        const float v = sobol_sample(table, shuffled_rev, dimension, hash);
         dimension += 1;
         return (double)v;
     }
+};
+
+// The eight sampler values of one path vertex, PathSegmentSamples::from (path_integrator.rs:25-36).  The reference draws all
+// eight up front; a value is a pure function of (sample index, dimension, pixel hash), so each is computed where -- and only
+// if -- it is consumed.
+struct VertexSamples {
+    const uint32_t* table;
+    uint32_t shuffled_rev, hash, first_dimension;
+    enum : uint32_t { MATERIAL_1D = 0, MATERIAL_U = 1, MATERIAL_V = 2, LIGHT_INDEX = 3, LIGHT_1D = 4, LIGHT_U = 5, LIGHT_V = 6, ROULETTE = 7 };
+    __device__ __forceinline__ double get(uint32_t k) const { return (double)sobol_sample(table, shuffled_rev, first_dimension + k, hash); }
 };
 
 // ---- sampling_fns sampling.rs:1-66 ----

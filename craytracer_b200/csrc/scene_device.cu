@@ -8,6 +8,7 @@
 #include <thread>
 
 #include "host_math.hpp"
+#include "sampler.cuh"
 #include "sobol_directions.h"
 
 namespace cray {
@@ -322,7 +323,20 @@ int cray_scene_create(const cray_scene_desc* d, int device, uint32_t build_flags
         for (uint32_t tx = 0; tx < cam.width; tx += 8)
             for (uint32_t y = ty; y < std::min(ty + 4, cam.height); ++y)
                 for (uint32_t x = tx; x < std::min(tx + 8, cam.width); ++x) pixel_order.push_back(x | (y << 16));
+    // Sobol direction vectors folded into byte tables (sampler.cuh:sobol_sample): [dimension][half][byte]
+#if !CRAY_SOBOL_BYTES
     std::vector<uint32_t> sobol(&SOBOL_DIRECTIONS_INIT[0][0], &SOBOL_DIRECTIONS_INIT[0][0] + 256 * 32);
+#else
+    std::vector<uint32_t> sobol(256 * 512);
+    for (uint32_t dim = 0; dim < 256; ++dim)
+        for (uint32_t half = 0; half < 2; ++half)
+            for (uint32_t b = 0; b < 256; ++b) {
+                uint32_t acc = 0;
+                for (uint32_t j = 0; j < 8; ++j)
+                    if (b & (0x80u >> j)) acc ^= SOBOL_DIRECTIONS_INIT[dim][8 * half + j];
+                sobol[dim * 512 + half * 256 + b] = acc;
+            }
+#endif
 
     SceneView& v = sc->view;
     const uint32_t* d_order = nullptr;

@@ -13,7 +13,7 @@ struct cray_scene {
     uint32_t build_flags = 0;
     cray::SceneView view{};
     std::vector<void*> allocations;    // every cudaMalloc of this scene
-    uint32_t* d_sobol = nullptr;       // SOBOL_DIRECTIONS[256][32]
+    uint32_t* d_sobol = nullptr;       // Sobol byte tables [256][2][256] (sampler.cuh)
     uint32_t* d_pixel_order = nullptr; // tile-ordered pixel list (x | y << 16)
     cray_scene_info info{};
     cudaStream_t stream = nullptr;     // calls on one handle are serialised on this stream

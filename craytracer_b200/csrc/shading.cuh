@@ -140,12 +140,12 @@ __device__ __forceinline__ PdfValue lobe_pdf(const DevLobe& l, V3 w_i, V3 normal
     return delta_pdf();
 }
 // BxDF::sample bxdf.rs:83-209
-__device__ __noinline__ bool lobe_sample(const SceneView& s, const DevLobe& l, double su, double sv, V3 w_o, V3 normal, double tu, double tv,
+__device__ __noinline__ bool lobe_sample(const SceneView& s, const DevLobe& l, const VertexSamples& vs, V3 w_o, V3 normal, double tu, double tv,
                                          SurfaceSample& out, bool& assert_failed) {
     switch (l.kind) {
         case LOBE_LAMBERTIAN:
         case LOBE_OREN_NAYAR: {
-            V3 w_i = cosine_sample_hemisphere(su, sv, normal, assert_failed);
+            V3 w_i = cosine_sample_hemisphere(vs.get(VertexSamples::MATERIAL_U), vs.get(VertexSamples::MATERIAL_V), normal, assert_failed);
             if (dot(normal, w_o) < 0.0) w_i = neg(w_i);
             out.w_i = w_i;
             out.f = lobe_f(s, l, w_o, w_i, normal, tu, tv);
@@ -190,7 +190,7 @@ __device__ __noinline__ bool lobe_sample(const SceneView& s, const DevLobe& l, d
         default: {  // LOBE_FRESNEL_SPECULAR bxdf.rs:176-207
             const double cos_theta_i = dot(w_o, normal);
             const double fresnel_reflectance = fresnel_dielectric(l.eta_i, l.eta_t, cos_theta_i);
-            if (su < fresnel_reflectance) {
+            if (vs.get(VertexSamples::MATERIAL_U) < fresnel_reflectance) {
                 out.w_i = reflect(w_o, normal);
                 out.f = eval_color(s, l.t0, tu, tv) * fresnel_reflectance / fabs(cos_theta_i);
                 out.pdf = non_delta(fresnel_reflectance);
@@ -236,13 +236,14 @@ __device__ __forceinline__ PdfValue material_pdf(const DevMaterial& m, V3 w_o, V
     return delta_pdf();
 }
 // Material::sample material.rs:72-83, BSDF::sample bsdf.rs:15-60
-__device__ __forceinline__ bool material_sample(const SceneView& s, const DevMaterial& m, double s1, double s2u, double s2v, V3 w_o, V3 normal,
+__device__ __forceinline__ bool material_sample(const SceneView& s, const DevMaterial& m, const VertexSamples& vs, V3 w_o, V3 normal,
                                                 double tu, double tv, SurfaceSample& out, bool& assert_failed) {
-    if (!m.is_bsdf) return lobe_sample(s, m.lobes[0], s2u, s2v, w_o, normal, tu, tv, out, assert_failed);
+    if (!m.is_bsdf) return lobe_sample(s, m.lobes[0], vs, w_o, normal, tu, tv, out, assert_failed);
     if (m.n_lobes == 0) return false;
-    const uint32_t sample_index = (uint32_t)as_usize(s1 * (double)m.n_lobes);
+    // one lobe: floor(u * 1) is 0 for every u in [0, 1)
+    const uint32_t sample_index = m.n_lobes == 1 ? 0u : (uint32_t)as_usize(vs.get(VertexSamples::MATERIAL_1D) * (double)m.n_lobes);
     SurfaceSample smp;
-    if (!lobe_sample(s, m.lobes[sample_index], s2u, s2v, w_o, normal, tu, tv, smp, assert_failed)) return false;
+    if (!lobe_sample(s, m.lobes[sample_index], vs, w_o, normal, tu, tv, smp, assert_failed)) return false;
     if (!smp.pdf.delta) {
         double pdf = smp.pdf.value;
         Color3 f = smp.f;
@@ -312,7 +313,7 @@ struct LightSample {  // light.rs:45-51
 };
 
 // Light::sample_Li light.rs:59-133
-__device__ __forceinline__ LightSample light_sample_li(const SceneView& s, const DevLight& l, double s1, double s2u, double s2v, V3 location, V3 normal,
+__device__ __forceinline__ LightSample light_sample_li(const SceneView& s, const DevLight& l, const VertexSamples& vs, V3 location, V3 normal,
                                                        bool& assert_failed) {
     LightSample out;
     const Color3 color = mkc(l.color[0], l.color[1], l.color[2]);
@@ -332,14 +333,14 @@ __device__ __forceinline__ LightSample light_sample_li(const SceneView& s, const
         out.Li = color;
         out.pdf = delta_pdf();
     } else if (l.kind == CRAY_LIGHT_INFINITE) {
-        const V3 n = s1 < 0.5 ? mk(1.0, 0.0, 0.0) : mk(-1.0, 0.0, 0.0);
-        out.w_i = sample_hemisphere(s2u, s2v, n);
+        const V3 n = vs.get(VertexSamples::LIGHT_1D) < 0.5 ? mk(1.0, 0.0, 0.0) : mk(-1.0, 0.0, 0.0);
+        out.w_i = sample_hemisphere(vs.get(VertexSamples::LIGHT_U), vs.get(VertexSamples::LIGHT_V), n);
         out.shadow_max = inf_f64();
         out.Li = color;
         out.pdf = non_delta(kFrac1Pi / 4.0);
     } else {
         // Shape::sample_from shape.rs:472-484
-        const V3 shape_point = shape_sample(s, l.shape, s2u, s2v);
+        const V3 shape_point = shape_sample(s, l.shape, vs.get(VertexSamples::LIGHT_U), vs.get(VertexSamples::LIGHT_V));
         out.w_i = normalized(shape_point - location);
         out.pdf = non_delta(shape_pdf_from(s, l.shape, l.area, location, normal, out.w_i));
         const double distance = magnitude(shape_point - location);

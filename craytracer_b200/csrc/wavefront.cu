@@ -479,17 +479,8 @@ __global__ void __launch_bounds__(128, CRAY_SHADE_MIN_BLOCKS) k_shade(SceneView 
     const cray_primitive_desc prim = s.prims[lp.prim];
     const DevMaterial& material = s.materials[prim.material];
 
-    // PathSegmentSamples::from path_integrator.rs:25-36 -- dimensions 4 + 8 * bounces ...
-    PixelSampler smp;
-    smp.hash = p.hash[i];
-    smp.shuffled_rev = p.shuffled_rev[i];
-    smp.dimension = 4u + 8u * bounces;
-    const double mat_1d = smp.sample_1d(job.sobol);
-    const double mat_u = smp.sample_1d(job.sobol), mat_v = smp.sample_1d(job.sobol);
-    const double light_index_1d = smp.sample_1d(job.sobol);
-    const double light_1d = smp.sample_1d(job.sobol);
-    const double light_u = smp.sample_1d(job.sobol), light_v = smp.sample_1d(job.sobol);
-    const double rr_1d = smp.sample_1d(job.sobol);
+    // PathSegmentSamples::from path_integrator.rs:25-36 -- dimensions 4 + 8 * bounces ... (evaluated where consumed)
+    const VertexSamples vs{job.sobol, p.shuffled_rev[i], p.hash[i], 4u + 8u * bounces};
 
     // emission (:106-126)
     if (prim.area_light >= 0) {
@@ -510,9 +501,10 @@ __global__ void __launch_bounds__(128, CRAY_SHADE_MIN_BLOCKS) k_shade(SceneView 
     bool shadow_pending = false;
     {
         double light_sampler_pdf;
-        const uint32_t light_index = light_pick(s, light_index_1d, light_sampler_pdf);
+        // a single light is picked whatever the sample value is (the search of light.rs:203-211 ends at 0 for every u < 1)
+        const uint32_t light_index = light_pick(s, s.n_lights > 1 ? vs.get(VertexSamples::LIGHT_INDEX) : 0.0, light_sampler_pdf);
         const DevLight& light = s.lights[light_index];
-        const LightSample ls = light_sample_li(s, light, light_1d, light_u, light_v, location, normal, bad);
+        const LightSample ls = light_sample_li(s, light, vs, location, normal, bad);
         Color3 contribution = mkc(0.0, 0.0, 0.0);
         const Color3 f = material_f(s, material, w_o, ls.w_i, normal, tu, tv);
         const double cos_theta = fabs(dot(ls.w_i, normal));
@@ -543,7 +535,7 @@ __global__ void __launch_bounds__(128, CRAY_SHADE_MIN_BLOCKS) k_shade(SceneView 
 
     // BSDF sample (:167-195)
     SurfaceSample ss;
-    if (!material_sample(s, material, mat_1d, mat_u, mat_v, w_o, normal, tu, tv, ss, bad)) { finish(L, shadow_pending); return; }
+    if (!material_sample(s, material, vs, w_o, normal, tu, tv, ss, bad)) { finish(L, shadow_pending); return; }
     if (is_black(ss.f)) { finish(L, shadow_pending); return; }
     const double cos_theta = fabs(dot(ss.w_i, normal));
     const double bsdf_pdf = ss.pdf.delta ? 1.0 : ss.pdf.value;
@@ -555,7 +547,7 @@ __global__ void __launch_bounds__(128, CRAY_SHADE_MIN_BLOCKS) k_shade(SceneView 
         const double max_beta_component = rmax(beta.r, rmax(beta.g, beta.b));
         if (max_beta_component < 1.0) {
             const double q = 1.0 - max_beta_component;
-            if (rr_1d < q) { finish(L, shadow_pending); return; }
+            if (vs.get(VertexSamples::ROULETTE) < q) { finish(L, shadow_pending); return; }
             beta = beta / (1.0 - q);
         }
     }
@@ -604,7 +596,7 @@ struct PoolStorage {
     WideTuning tune{8, 8};
     unsigned shadow_blocks = 0;       // the any-hit instantiation needs fewer registers: its own occupancy
     unsigned long long* d_trace_counters = nullptr;  // {n, cursor} for the S3 entry points
-    std::vector<cudaEvent_t> timers;                 // (start, stop) of every extend launch of one render, reused across calls
+    std::vector<cudaEvent_t> timers;                 // stage boundaries of every iteration of one render, reused across calls
 };
 
 int ensure_pool(cray_scene* sc, uint32_t capacity) {
@@ -667,26 +659,30 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
     // The host never waits for traversal or shading: it enqueues the whole iteration, then waits only for the iteration's
     // k_generate (long finished by the time the GPU works through extend / shade / shadow) to learn whether any path is
     // still alive.  The three launches behind the last, empty generate find empty queues and return at once.
+    constexpr size_t kMarks = 5;  // per iteration: before generate | extend | shade | shadow | after shadow
     for (size_t iter = 0;; ++iter) {
-        CRAY_CUDA(cudaMemsetAsync(&dc->n_extend, 0, per_iteration, stream));
-        k_generate<<<g256, 256, 0, stream>>>(sc->view, pool, job, dc);
-        CRAY_CUDA(cudaMemcpyAsync(ps->h_counters, dc, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-        CRAY_CUDA(cudaEventRecord(gen_done, stream));
         if (timed) {
-            while (ps->timers.size() < 2 * (iter + 1)) {
+            while (ps->timers.size() < kMarks * (iter + 1)) {
                 cudaEvent_t ev;
                 CRAY_CUDA(cudaEventCreate(&ev));
                 ps->timers.push_back(ev);
             }
-            CRAY_CUDA(cudaEventRecord(ps->timers[2 * iter], stream));
+            CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter], stream));
         }
+        CRAY_CUDA(cudaMemsetAsync(&dc->n_extend, 0, per_iteration, stream));
+        k_generate<<<g256, 256, 0, stream>>>(sc->view, pool, job, dc);
+        CRAY_CUDA(cudaMemcpyAsync(ps->h_counters, dc, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+        CRAY_CUDA(cudaEventRecord(gen_done, stream));
+        if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 1], stream));
         if (job.exact) k_extend_exact<<<g128, 128, 0, stream>>>(sc->view, pool, &dc->n_extend);
         else k_wide_persistent<false, ExtendSource><<<gp, 128, 0, stream>>>(sc->view, ExtendSource{pool}, &dc->n_extend, &dc->extend_cursor, ps->tune);
-        if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[2 * iter + 1], stream));
+        if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 2], stream));
         k_shade<<<g128, 128, 0, stream>>>(sc->view, pool, job, dc);
+        if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 3], stream));
         // at most one shadow ray per shaded vertex; the queue length lives on the device
         if (job.exact) k_shadow_exact<<<g128, 128, 0, stream>>>(sc->view, pool, &dc->n_shadow);
         else k_wide_persistent<true, ShadowSource><<<gs, 128, 0, stream>>>(sc->view, ShadowSource{pool}, &dc->n_shadow, &dc->shadow_cursor, ps->tune);
+        if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 4], stream));
         launches += 4;
         CRAY_CUDA(cudaEventSynchronize(gen_done));
         const uint64_t live = ps->h_counters->n_extend;
@@ -700,12 +696,13 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
     float ms = 0;
     CRAY_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     if (stats) {
-        double trace_ms = 0.0;
-        for (size_t i = 0; i < iterations; ++i) {
-            float t = 0;
-            CRAY_CUDA(cudaEventElapsedTime(&t, ps->timers[2 * i], ps->timers[2 * i + 1]));
-            trace_ms += t;
-        }
+        double part[4] = {0.0, 0.0, 0.0, 0.0};  // generate, extend, shade, shadow
+        for (size_t i = 0; i < iterations; ++i)
+            for (size_t k = 0; k < 4; ++k) {
+                float t = 0;
+                CRAY_CUDA(cudaEventElapsedTime(&t, ps->timers[kMarks * i + k], ps->timers[kMarks * i + k + 1]));
+                part[k] += t;
+            }
         stats->samples = job.n_total;
         stats->closest_rays = closest;
         stats->shadow_rays = ps->h_counters->shadow_rays;
@@ -713,7 +710,10 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
         stats->iterations = iterations;
         stats->kernel_launches = launches;
         stats->render_ms = ms;
-        stats->trace_ms = trace_ms;
+        stats->generate_ms = part[0];
+        stats->trace_ms = part[1];
+        stats->shade_ms = part[2];
+        stats->shadow_ms = part[3];
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(gen_done);
     return CRAY_OK;

@@ -197,7 +197,10 @@ typedef struct cray_render_stats {
     uint64_t iterations;       /* wavefront iterations */
     uint64_t kernel_launches;  /* kernels launched by this call */
     double render_ms;          /* device time of the render region (CUDA events) */
-    double trace_ms;           /* device time inside the closest-hit + any-hit kernels */
+    double trace_ms;           /* device time inside the closest-hit (extend) traversal launches */
+    double shadow_ms;          /* ... inside the any-hit (shadow) traversal launches */
+    double shade_ms;           /* ... inside the shading launches */
+    double generate_ms;        /* ... inside the flush / camera-ray launches */
 } cray_render_stats;
 
 /* Samples [sample_begin, sample_end) of every pixel; film is the SUM over those samples

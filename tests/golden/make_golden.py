@@ -28,12 +28,17 @@ def scene_table():
     def dragon_small():
         c.register_standin_mesh("objs/xyzrgb_dragon.obj", 0, 30001, 0)
         return c.parse_scene(scenes.dragon(width=96, height=64), base_dir="/nonexistent")
+    def staircase_small():
+        # scenes/staircase.cry over the stand-in assets (assets/objs/staircase: 26 MTL materials, 10 image textures, thin lens)
+        c.register_standin_mesh("objs/staircase/staircase.obj", 1, 20000, 0)
+        return c.parse_scene(scenes.staircase(width=48, height=80), base_dir=os.path.join(ROOT, "assets"))
     return {
         "simple": (lambda: c.parse_scene(scenes.simple(width=96, height=56)), [-45, -1, -35], [45, 12, 55]),
         "materials": (lambda: c.parse_scene(scenes.materials(width=96, height=64)), [-8, -1, -6], [12, 16, 16]),
         "test": (lambda: c.parse_scene(scenes.test_scene(width=64, height=64)), [-1, -1, -3], [4, 3, 1]),
         "rounding-error": (lambda: c.parse_scene(scenes.rounding_error(width=64, height=64)), [-10, -1, -10], [10, 8, 10]),
         "dragon_small": (dragon_small, [-120, -45, -60], [120, 60, 60]),
+        "staircase_small": (staircase_small, [-1.6, -0.1, -2.1], [1.6, 5.6, 3.1]),
         # scenes/cornell.cry over the authored stand-in mesh (assets/objs/local/cornell)
         "cornell": (lambda: c.parse_scene(scenes.cornell(width=64, height=64), base_dir=os.path.join(ROOT, "assets")), [-1.1, -0.1, -1.1], [1.1, 2.1, 1.1]),
     }

@@ -17,6 +17,8 @@ SCENES = {
     "test": (lambda: c.parse_scene(scenes.test_scene(width=128, height=128)), [-1, -1, -3], [4, 3, 1]),
     "rounding-error": (lambda: c.parse_scene(scenes.rounding_error(width=128, height=128)), [-10, -1, -10], [10, 8, 10]),
     "dragon_small": (None, [-120, -45, -60], [120, 60, 60]),
+    # scenes/staircase.cry over the stand-in assets: 26 MTL materials (plastic / conductor / glass), 10 image textures, thin lens
+    "staircase_small": (None, [-1.6, -0.1, -2.1], [1.6, 5.6, 3.1]),
     # scenes/cornell.cry over the authored stand-in mesh; planar walls coincide with BVH box faces, so the reference's AABB rule
     # produces false misses here too (SURVEY A-4b)
     "cornell": (lambda: c.parse_scene(scenes.cornell(width=96, height=96), base_dir=scenes.ASSETS), [-1.1, -0.1, -1.1], [1.1, 2.1, 1.1]),
@@ -32,9 +34,14 @@ def _dragon_small():
 _cache = {}
 
 
+def _staircase_small():
+    c.register_standin_mesh("objs/staircase/staircase.obj", 1, 20000, 0)
+    return c.parse_scene(scenes.staircase(width=72, height=128), base_dir=scenes.ASSETS)
+
+
 def get_scene(name):
     if name not in _cache:
-        hs = _dragon_small() if name == "dragon_small" else SCENES[name][0]()
+        hs = _dragon_small() if name == "dragon_small" else (_staircase_small() if name == "staircase_small" else SCENES[name][0]())
         _cache[name] = (hs, c.Scene(hs), o.OracleScene(hs))
     return _cache[name]
 
@@ -152,7 +159,7 @@ def test_reference_false_miss_is_reproduced_only_by_exact_mode(name):
 
 
 @pytest.mark.parametrize("mode,mode_name", MODES)
-@pytest.mark.parametrize("name", ["simple", "materials", "test", "dragon_small"])
+@pytest.mark.parametrize("name", ["simple", "materials", "test", "dragon_small", "staircase_small"])
 def test_radiance_samples_match_oracle(name, mode, mode_name):
     """S2: render_pixel + estimate_Li per (x, y, sample).  Same sampler integers on both sides, f64 shading with the
     reference's operation order: samples agree to ~1e-12; only libm-vs-CUDA ulp differences in sin/cos/atan2 remain."""
@@ -169,7 +176,7 @@ def test_radiance_samples_match_oracle(name, mode, mode_name):
         assert abs(got.mean() - ref.mean()) <= 2e-3 * abs(ref.mean()) + 1e-12
 
 
-@pytest.mark.parametrize("name", ["simple", "materials", "test", "rounding-error", "dragon_small"])
+@pytest.mark.parametrize("name", ["simple", "materials", "test", "rounding-error", "dragon_small", "staircase_small"])
 def test_film_matches_oracle_exact_mode(name):
     """S1 at equal spp: the exact mode renders the oracle's film (f32 sums; accumulation order is the only difference)."""
     hs, gpu, orc = get_scene(name)
@@ -183,7 +190,7 @@ def test_film_matches_oracle_exact_mode(name):
     assert np.abs(film - ref).max() <= 1e-4 * max(1.0, float(ref.max()))
 
 
-@pytest.mark.parametrize("name", ["simple", "materials", "dragon_small"])
+@pytest.mark.parametrize("name", ["simple", "materials", "dragon_small", "staircase_small"])
 def test_film_fast_mode_within_relative_mse(name):
     """Production (wide BVH) mode vs the oracle at equal spp.  Tolerance: relMSE <= 1e-4 and channel means within 0.5 %
     (SURVEY 8d); on these scenes the two agree far better because the sample sets are identical."""
