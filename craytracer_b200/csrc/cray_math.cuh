@@ -52,6 +52,17 @@ CRAY_HD uint32_t as_u32(double x) {
     return (uint32_t)x;
 }
 
+// f64 division and square root expand to ~25 instructions each.  The shading code has hundreds of call sites, and its
+// instruction-cache misses cost more than a call does, so the vector / colour operators below go through ONE out-of-line copy
+// on the device (same IEEE result).  The traversal kernels divide scalars directly and stay inline.
+#if defined(__CUDA_ARCH__) && !defined(CRAY_INLINE_DIV)
+static __device__ __noinline__ double div_rn(double a, double b) { return a / b; }
+static __device__ __noinline__ double sqrt_rn(double a) { return sqrt(a); }
+#else
+CRAY_HD double div_rn(double a, double b) { return a / b; }
+CRAY_HD double sqrt_rn(double a) { return sqrt(a); }
+#endif
+
 struct V3 {
     double x, y, z;
     CRAY_HD double operator[](int a) const { return a == 0 ? x : (a == 1 ? y : z); }
@@ -60,14 +71,14 @@ CRAY_HD V3 mk(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; r
 CRAY_HD V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
 CRAY_HD V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
 CRAY_HD V3 operator*(V3 a, double s) { return mk(a.x * s, a.y * s, a.z * s); }
-CRAY_HD V3 operator/(V3 a, double s) { return mk(a.x / s, a.y / s, a.z / s); }
+CRAY_HD V3 operator/(V3 a, double s) { return mk(div_rn(a.x, s), div_rn(a.y, s), div_rn(a.z, s)); }
 CRAY_HD V3 neg(V3 a) { return a * -1.0; }  // Neg is `self * -1.0` (geometry.rs:155)
 CRAY_HD double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 CRAY_HD double magnitude_squared(V3 a) { return dot(a, a); }
-CRAY_HD double magnitude(V3 a) { return sqrt(magnitude_squared(a)); }
+CRAY_HD double magnitude(V3 a) { return sqrt_rn(magnitude_squared(a)); }
 CRAY_HD V3 normalized(V3 a) {
     double mag = magnitude(a);
-    return mk(a.x / mag, a.y / mag, a.z / mag);
+    return mk(div_rn(a.x, mag), div_rn(a.y, mag), div_rn(a.z, mag));
 }
 CRAY_HD V3 cross(V3 a, V3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 CRAY_HD bool same_hemisphere(V3 n, V3 v1, V3 v2) { return dot(n, v1) * dot(n, v2) > 0.0; }  // geometry.rs:403
@@ -88,9 +99,9 @@ CRAY_HD Color3 mkc(double r, double g, double b) { Color3 c; c.r = r; c.g = g; c
 CRAY_HD Color3 operator+(Color3 a, Color3 c) { return mkc(a.r + c.r, a.g + c.g, a.b + c.b); }
 CRAY_HD Color3 operator-(Color3 a, Color3 c) { return mkc(a.r - c.r, a.g - c.g, a.b - c.b); }
 CRAY_HD Color3 operator*(Color3 a, Color3 c) { return mkc(a.r * c.r, a.g * c.g, a.b * c.b); }
-CRAY_HD Color3 operator/(Color3 a, Color3 c) { return mkc(a.r / c.r, a.g / c.g, a.b / c.b); }
+CRAY_HD Color3 operator/(Color3 a, Color3 c) { return mkc(div_rn(a.r, c.r), div_rn(a.g, c.g), div_rn(a.b, c.b)); }
 CRAY_HD Color3 operator*(Color3 a, double s) { return mkc(a.r * s, a.g * s, a.b * s); }
-CRAY_HD Color3 operator/(Color3 a, double s) { return mkc(a.r / s, a.g / s, a.b / s); }
+CRAY_HD Color3 operator/(Color3 a, double s) { return mkc(div_rn(a.r, s), div_rn(a.g, s), div_rn(a.b, s)); }
 CRAY_HD bool is_black(Color3 c) { return c.r == 0.0 && c.g == 0.0 && c.b == 0.0; }
 CRAY_HD bool finite_f64(double x) { return fabs(x) <= 1.7976931348623157e308; }  // false for +-inf and NaN
 CRAY_HD bool is_finite3(Color3 c) { return finite_f64(c.r) && finite_f64(c.g) && finite_f64(c.b); }

@@ -16,7 +16,7 @@ enum : uint32_t { PRIM_SPHERE = CRAY_SHAPE_SPHERE, PRIM_TRIANGLE = CRAY_SHAPE_TR
 struct alignas(16) LeafPrim {
     double d[9];
     uint32_t prim;   // index in reference primitive order
-    uint32_t kind;   // PRIM_* | aux << 8
+    uint32_t kind;   // PRIM_* | shade class << 8 (k_shade groups paths by it) | disk index << 16
 };
 static_assert(sizeof(LeafPrim) == 80, "LeafPrim layout");
 

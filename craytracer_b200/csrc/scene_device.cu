@@ -58,9 +58,12 @@ LeafPrim make_leaf_prim(const cray_scene_desc& d, uint32_t prim) {
             break;
         }
         default:
-            lp.kind = PRIM_DISK | (p.shape_index << 8);
+            lp.kind = PRIM_DISK | (p.shape_index << 16);
             break;
     }
+    // shade class: which family of shading code a hit on this primitive runs (area lights carry a black matte, primitive.rs:43-46)
+    const uint32_t shade_class = p.area_light >= 0 ? (uint32_t)CRAY_MAT_MATTE : d.materials[p.material].kind;
+    lp.kind |= (shade_class & 0xFFu) << 8;
     return lp;
 }
 
@@ -134,6 +137,7 @@ int validate(const cray_scene_desc* d) {
     if (d->n_primitives == 0) { set_error("scene has no primitives"); return CRAY_E_INVALID; }
     if (d->n_lights == 0) { set_error("No lights in the scene."); return CRAY_E_INVALID; }  // scene_parser.rs:1103
     if (d->n_primitives >= 0xFFFFFFF0ull) { set_error("too many primitives"); return CRAY_E_INVALID; }
+    if (d->n_disks > 0xFFFFull) { set_error("more than 65535 disks"); return CRAY_E_UNSUPPORTED; }
     if (d->camera.width == 0 || d->camera.height == 0 || d->camera.width > 65535 || d->camera.height > 65535) { set_error("film size out of range"); return CRAY_E_INVALID; }
     for (uint64_t i = 0; i < d->n_primitives; ++i) {
         const cray_primitive_desc& p = d->primitives[i];

@@ -69,7 +69,7 @@ __device__ __forceinline__ double fresnel_dielectric(double eta_i, double eta_t,
     const double r_perpendicular = (eta_i * cos_theta_i - eta_t * cos_theta_t) / (eta_i * cos_theta_i + eta_t * cos_theta_t);
     return (r_parallel * r_parallel + r_perpendicular * r_perpendicular) * 0.5;
 }
-__device__ __forceinline__ Color3 csqrt(Color3 c) { return mkc(sqrt(c.r), sqrt(c.g), sqrt(c.b)); }  // powf(0.5) lowers to sqrt
+__device__ __forceinline__ Color3 csqrt(Color3 c) { return mkc(sqrt_rn(c.r), sqrt_rn(c.g), sqrt_rn(c.b)); }  // powf(0.5) lowers to sqrt
 __device__ __forceinline__ Color3 fresnel_conductor(Color3 eta_i, Color3 eta_t, Color3 k, double cos_theta_i) {  // :359-382
     const Color3 white = mkc(1.0, 1.0, 1.0);
     const Color3 eta_rel = eta_t / eta_i;
@@ -278,7 +278,7 @@ __device__ __forceinline__ V3 shape_sample(const SceneView& s, const LeafPrim& s
         const double b1 = 1.0 - su_sqrt, b2 = sv * su_sqrt;
         return mk(sh.d[0], sh.d[1], sh.d[2]) + mk(sh.d[3], sh.d[4], sh.d[5]) * b1 + mk(sh.d[6], sh.d[7], sh.d[8]) * b2;
     }
-    const DiskXf& k = s.disks[sh.kind >> 8];
+    const DiskXf& k = s.disks[sh.kind >> 16];
     double x, y;
     sample_disk(su, sv, x, y);
     return xf_point(k.o2w, mk(x * k.radius, y * k.radius, 0.0));

@@ -426,13 +426,63 @@ __global__ void __launch_bounds__(128) k_extend_exact(SceneView s, Pool p, const
 }
 
 // One iteration of the `while` loop of estimate_Li (path_integrator.rs:54-212) for one path.
-#ifndef CRAY_SHADE_MIN_BLOCKS
-#define CRAY_SHADE_MIN_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(128, CRAY_SHADE_MIN_BLOCKS) k_shade(SceneView s, Pool p, Job job, Counters* counters) {
-    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= counters->n_extend) return;
-    const uint32_t i = p.extend_queue[q];
+//
+// Paths of one block are first grouped by (shade class, shape kind) of what they hit -- a counting sort of the block's 256
+// queue entries in shared memory -- so that the lanes of a warp run the same material / surface code.
+constexpr uint32_t kShadeThreads = 256;
+constexpr uint32_t kShadeKeys = 16;   // class (matte, glass, plastic, metal) x shape kind (3); 12 = miss; 13 = no path
+
+__global__ void __launch_bounds__(kShadeThreads, 2) k_shade(SceneView s, Pool p, Job job, Counters* counters) {
+    constexpr uint32_t kWarps = kShadeThreads / 32, kCells = kShadeKeys * kWarps;  // 128 (key, warp) cells
+    __shared__ uint32_t s_count[kCells];
+    __shared__ uint32_t s_warp_total[kCells / 32];
+    __shared__ uint32_t s_order[kShadeThreads];
+    const uint64_t n_extend = counters->n_extend;
+    if ((uint64_t)blockIdx.x * kShadeThreads >= n_extend) return;  // whole block idle
+    uint32_t i, slot;
+    {
+        const uint64_t q = (uint64_t)blockIdx.x * kShadeThreads + threadIdx.x;
+        const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+        uint32_t mine = 0xFFFFFFFFu, key = 13u;
+        if (q < n_extend) {
+            mine = p.extend_queue[q];
+            const uint32_t my_slot = p.hit_slot[mine];
+            key = 12u;
+            if (my_slot != CRAY_NO_HIT) {
+                const uint32_t kind = __ldg(&(job.exact ? s.bin_prims : s.wide_prims)[my_slot].kind);
+                key = ((kind >> 8) & 3u) * 3u + (kind & 3u);
+            }
+        }
+        if (threadIdx.x < kCells) s_count[threadIdx.x] = 0u;
+        __syncthreads();
+        const unsigned grp = __match_any_sync(0xFFFFFFFFu, key);
+        if (lane == (unsigned)(__ffs(grp) - 1)) s_count[key * kWarps + warp] = __popc(grp);
+        __syncthreads();
+        // exclusive scan of the cells in (key, warp) order: the first kCells / 32 warps scan 32 cells each
+        uint32_t cell = 0, incl = 0;
+        if (threadIdx.x < kCells) {
+            cell = s_count[threadIdx.x];
+            incl = cell;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= (unsigned)d) incl += up;
+            }
+            if (lane == 31u) s_warp_total[warp] = incl;
+        }
+        __syncthreads();
+        if (threadIdx.x < kCells) {
+            uint32_t before = 0;
+            for (uint32_t w = 0; w < warp; ++w) before += s_warp_total[w];
+            s_count[threadIdx.x] = before + incl - cell;
+        }
+        __syncthreads();
+        s_order[s_count[key * kWarps + warp] + __popc(grp & ((1u << lane) - 1u))] = mine;
+        __syncthreads();
+        i = s_order[threadIdx.x];
+        if (i == 0xFFFFFFFFu) return;
+        slot = p.hit_slot[i];
+    }
     uint32_t st = p.state[i];
     const uint32_t bounces = st_bounces(st);
     const bool is_specular_bounce = (st >> 16) & 1u;
@@ -442,7 +492,6 @@ __global__ void __launch_bounds__(128, CRAY_SHADE_MIN_BLOCKS) k_shade(SceneView 
     Color3 L = mkc(p.L_r[i], p.L_g[i], p.L_b[i]);
     Color3 beta = mkc(p.beta_r[i], p.beta_g[i], p.beta_b[i]);
     const double prev_bsdf_pdf = p.prev_bsdf_pdf[i];
-    const uint32_t slot = p.hit_slot[i];
 
     auto finish = [&](Color3 Lf, bool shadow_pending) {
         p.L_r[i] = Lf.r; p.L_g[i] = Lf.g; p.L_b[i] = Lf.b;
@@ -677,7 +726,7 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
         if (job.exact) k_extend_exact<<<g128, 128, 0, stream>>>(sc->view, pool, &dc->n_extend);
         else k_wide_persistent<false, ExtendSource><<<gp, 128, 0, stream>>>(sc->view, ExtendSource{pool}, &dc->n_extend, &dc->extend_cursor, ps->tune);
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 2], stream));
-        k_shade<<<g128, 128, 0, stream>>>(sc->view, pool, job, dc);
+        k_shade<<<(capacity + kShadeThreads - 1) / kShadeThreads, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 3], stream));
         // at most one shadow ray per shaded vertex; the queue length lives on the device
         if (job.exact) k_shadow_exact<<<g128, 128, 0, stream>>>(sc->view, pool, &dc->n_shadow);
@@ -905,7 +954,9 @@ int cray_render_device(cray_scene* sc, int mode, uint64_t seed, uint32_t sample_
         job.film = ps->d_film;
         job.sobol = sc->d_sobol;
         job.exact = mode == CRAY_TRAVERSE_EXACT;
-        const uint32_t capacity = (uint32_t)std::min<uint64_t>(n_total, 1u << 21);
+        uint32_t pool_log2 = 23;  // path slots in flight (1.7 GB of path state); CRAY_POOL_LOG2 overrides it for tuning
+        if (const char* e = std::getenv("CRAY_POOL_LOG2")) pool_log2 = (uint32_t)std::max(10, std::min(26, std::atoi(e)));
+        const uint32_t capacity = (uint32_t)std::min<uint64_t>(n_total, 1ull << pool_log2);
         rc = run_wavefront(sc, job, capacity, stream, stats);
         if (rc != CRAY_OK) return rc;
     }
