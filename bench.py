@@ -272,7 +272,8 @@ def run_ours(args):
                          "rays_in_kernel": totals["closest"], "kernel_ms": extend_ms, "kernel_share_of_step": extend_ms / max(totals["render_ms"], 1e-9),
                          "traffic": traffic},
             "stage_ms_per_step": {"extend": totals["trace_ms"] / args.steps, "shade": totals["shade_ms"] / args.steps, "shadow": totals["shadow_ms"] / args.steps,
-                                  "generate": totals["generate_ms"] / args.steps, "iterations": totals["iters"] / args.steps},
+                                  "generate": totals["generate_ms"] / args.steps, "render_call": totals["render_ms"] / args.steps,
+                                  "iterations": totals["iters"] / args.steps},
             "clocks": clocks,
             "setup": {"parse_and_standin_s": parse_s, "bvh_build_ms": scene.info.bvh_build_ms, "upload_ms": scene.info.upload_ms, "scene_create_s": create_s,
                       "wide_nodes": scene.info.wide_nodes, "wide_depth": scene.info.wide_depth, "triangles": hs.desc.n_triangles},

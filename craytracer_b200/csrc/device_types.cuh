@@ -42,6 +42,8 @@ struct DevLobe {     // BxDF, bxdf.rs:23-50
 };
 struct DevMaterial { // Material, material.rs:13-17
     uint32_t is_bsdf, n_lobes;
+    uint32_t needs_uv;         // some texture of some lobe is not a constant: the hit's texture coordinates are read
+    uint32_t all_delta;        // every lobe is a perfect-specular one: BxDF::f is black for every direction (bxdf.rs:259-264)
     DevLobe lobes[2];
 };
 struct DevImage {

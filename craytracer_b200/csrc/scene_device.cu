@@ -113,6 +113,11 @@ DevMaterial make_material(const cray_material_desc& m) {  // Material::new_* mat
             r.lobes[0] = lobe(LOBE_CONDUCTOR, m.t0, m.t1, m.t2, 1.0, 1.0);
             break;
     }
+    r.all_delta = 1;
+    for (uint32_t i = 0; i < r.n_lobes; ++i)
+        if (r.lobes[i].kind == LOBE_LAMBERTIAN || r.lobes[i].kind == LOBE_OREN_NAYAR) r.all_delta = 0;
+    for (uint32_t i = 0; i < r.n_lobes; ++i)
+        if (r.lobes[i].t0.kind != CRAY_TEX_CONSTANT || r.lobes[i].t1.kind != CRAY_TEX_CONSTANT || r.lobes[i].sigma.kind != CRAY_TEX_CONSTANT) r.needs_uv = 1;
     return r;
 }
 

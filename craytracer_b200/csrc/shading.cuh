@@ -293,7 +293,7 @@ __device__ __forceinline__ double shape_pdf_from(const SceneView& s, const LeafP
     // only the location is needed; recompute it the way Shape::intersect does
     const uint32_t kind = sh.kind & 0xFFu;
     if (kind == PRIM_TRIANGLE) hit_location = location + w_i * ray_max;
-    else surface_at(s, sh, location, w_i, ray_max, u, v, hit_location, hit_normal, tu, tv);
+    else surface_at(s, sh, location, w_i, ray_max, u, v, hit_location, hit_normal, tu, tv, false);
     const double distance_squared = magnitude_squared(hit_location - location);
     const double cos_theta = fabs(dot(w_i, normal));
     return distance_squared / (cos_theta * area);

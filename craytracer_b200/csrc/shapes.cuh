@@ -152,27 +152,34 @@ __device__ __forceinline__ int leaf_prim_candidate(const SceneView& s, const Lea
     return 0;
 }
 
-// The rest of PrimitiveIntersection (location, normal, uv) for an accepted hit at distance t.
+// The rest of PrimitiveIntersection (location, normal, uv) for an accepted hit at distance t.  `want_uv` = false skips the
+// texture coordinates (atan2 / acos on spheres and disks): nothing reads them when every texture of the material hit is a
+// constant, and the light's self-intersection test (shape.rs:487-502) only needs the location.
 __device__ __forceinline__ void surface_at(const SceneView& s, const LeafPrim& lp, V3 o, V3 dir, double t, double bu, double bv,
-                                           V3& location, V3& normal, double& tex_u, double& tex_v) {
+                                           V3& location, V3& normal, double& tex_u, double& tex_v, bool want_uv = true) {
     const uint32_t kind = lp.kind & 0xFFu;
+    tex_u = 0.0; tex_v = 0.0;
     if (kind == PRIM_TRIANGLE) {  // shape.rs:249-258
         const TriShade& ts = s.tri_shade[s.prims[lp.prim].shape_index];
         location = o + dir * t;
         const V3 n0 = mk(ts.n0[0], ts.n0[1], ts.n0[2]), n01 = mk(ts.n01[0], ts.n01[1], ts.n01[2]), n02 = mk(ts.n02[0], ts.n02[1], ts.n02[2]);
         normal = normalized(n0 + n01 * bu + n02 * bv);
-        tex_u = ts.uv0[0] + ts.uv01[0] * bu + ts.uv02[0] * bv;
-        tex_v = ts.uv0[1] + ts.uv01[1] * bu + ts.uv02[1] * bv;
+        if (want_uv) {
+            tex_u = ts.uv0[0] + ts.uv01[0] * bu + ts.uv02[0] * bv;
+            tex_v = ts.uv0[1] + ts.uv01[1] * bu + ts.uv02[1] * bv;
+        }
         return;
     }
     if (kind == PRIM_SPHERE) {  // shape.rs:178-195
         const V3 oc = mk(o.x + (-lp.d[0]), o.y + (-lp.d[1]), o.z + (-lp.d[2]));
         const double radius = lp.d[3];
         const V3 loc = oc + dir * t;
-        double phi = atan2(loc.y, loc.x);
-        if (phi < 0.0) phi += kPi * 2.0;
-        tex_u = phi / (kPi * 2.0);
-        tex_v = acos(loc.z / radius) * kFrac1Pi;
+        if (want_uv) {
+            double phi = atan2(loc.y, loc.x);
+            if (phi < 0.0) phi += kPi * 2.0;
+            tex_u = phi / (kPi * 2.0);
+            tex_v = acos(loc.z / radius) * kFrac1Pi;
+        }
         location = mk(loc.x + lp.d[0], loc.y + lp.d[1], loc.z + lp.d[2]);  // object_to_world = translate(origin)
         normal = loc / radius;                                               // inverse-transpose of a translation is the identity
         return;
@@ -181,11 +188,13 @@ __device__ __forceinline__ void surface_at(const SceneView& s, const LeafPrim& l
     const V3 oo = xf_point(k.w2o, o);
     const V3 od = xf_vector(k.w2o, dir);
     const double lx = oo.x + od.x * t, ly = oo.y + od.y * t;
-    const double d2 = lx * lx + ly * ly;
-    double theta = atan2(ly, lx);
-    if (theta < 0.0) theta += kPi * 2.0;
-    tex_u = theta / (kPi * 2.0);
-    tex_v = sqrt(d2) / k.radius;
+    if (want_uv) {
+        const double d2 = lx * lx + ly * ly;
+        double theta = atan2(ly, lx);
+        if (theta < 0.0) theta += kPi * 2.0;
+        tex_u = theta / (kPi * 2.0);
+        tex_v = sqrt(d2) / k.radius;
+    }
     location = xf_point(k.o2w, mk(lx, ly, 0.0));
     normal = xf_normal_with_inverse(k.w2o, mk(0.0, 0.0, 1.0));
 }

@@ -524,9 +524,9 @@ __global__ void __launch_bounds__(kShadeThreads, 2) k_shade(SceneView s, Pool p,
         double t2;
         triangle_eval(lp.d, ro, rd, t2, bu, bv);
     }
-    surface_at(s, lp, ro, rd, hit_t, bu, bv, location, normal, tu, tv);
     const cray_primitive_desc prim = s.prims[lp.prim];
     const DevMaterial& material = s.materials[prim.material];
+    surface_at(s, lp, ro, rd, hit_t, bu, bv, location, normal, tu, tv, material.needs_uv != 0u);
 
     // PathSegmentSamples::from path_integrator.rs:25-36 -- dimensions 4 + 8 * bounces ... (evaluated where consumed)
     const VertexSamples vs{job.sobol, p.shuffled_rev[i], p.hash[i], 4u + 8u * bounces};
@@ -546,9 +546,12 @@ __global__ void __launch_bounds__(kShadeThreads, 2) k_shade(SceneView s, Pool p,
         }
     }
 
-    // next-event estimation (:129-164): the shadow ray is traced by k_shadow, the contribution is parked
+    // next-event estimation (:129-164): the shadow ray is traced by the shadow stage, the contribution is parked.
+    // Where every lobe of the material is perfectly specular, Material::f is black for every direction, so the light sample
+    // cannot contribute: it is not drawn (the reference's shadow ray, :141, is still counted).
     bool shadow_pending = false;
-    {
+    warp_count(&counters->shadow_rays, true);
+    if (!material.all_delta) {
         double light_sampler_pdf;
         // a single light is picked whatever the sample value is (the search of light.rs:203-211 ends at 0 for every u < 1)
         const uint32_t light_index = light_pick(s, s.n_lights > 1 ? vs.get(VertexSamples::LIGHT_INDEX) : 0.0, light_sampler_pdf);
@@ -568,9 +571,7 @@ __global__ void __launch_bounds__(kShadeThreads, 2) k_shade(SceneView s, Pool p,
         } else {
             contribution = beta * ls.Li * f * cos_theta / light_sampler_pdf;
         }
-        // the reference always casts the shadow ray (:141); it is counted as a ray here too, but only traced when an
-        // unoccluded result could change L
-        warp_count(&counters->shadow_rays, true);
+        // traced only when an unoccluded result could change L
         if (!is_black(contribution) || !is_finite3(contribution)) {
             shadow_pending = true;
             queue_append(&counters->n_shadow, p.shadow_queue, i);
