@@ -46,53 +46,97 @@ def profiled_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock and throttle reasons sampled every 250 ms DURING the timed region.  NVML is read in-process (pynvml): the
+    `nvidia-smi -lms` loop of the profiling recipe costs this workload ~4 % (its query takes driver locks that delay the ~100
+    kernel launches of a frame); nvidia-smi remains the fallback when pynvml is missing."""
 
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.sm, self.smax, self.reasons = [], [], set()
+        self.source = None
+
+    def _nvml_loop(self, nv, handle):
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                self.smax.append(float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)))
+                mask = int(get_reasons(handle))
+                for name, bit in bits.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.25)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            index = self.gpu
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if visible:
+                try:
+                    index = int(visible.split(",")[self.gpu])
+                except Exception:
+                    pass
+            handle = nv.nvmlDeviceGetHandleByIndex(index)
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.source = "nvidia-smi"
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "500"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for line in open(self.path):
-                parts = [p.strip() for p in line.split(",")]
-                if len(parts) < 9:
-                    continue
-                try:
-                    sm.append(float(parts[1]))
-                    smax.append(float(parts[2]))
-                except ValueError:
-                    continue
-                for name, val in zip(names, parts[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(smax)) if smax else None, "reasons": sorted(reasons), "samples": len(sm)}
+        if self.thread:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+        elif self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            try:
+                for line in open(self.path):
+                    parts = [p.strip() for p in line.split(",")]
+                    if len(parts) < 9:
+                        continue
+                    try:
+                        self.sm.append(float(parts[1]))
+                        self.smax.append(float(parts[2]))
+                    except ValueError:
+                        continue
+                    for name, val in zip(self.NAMES, parts[5:9]):
+                        if val.lower().startswith("active"):
+                            self.reasons.add(name)
+                os.unlink(self.path)
+            except Exception:
+                pass
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source"]}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": float(max(self.smax)) if self.smax else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 def build_host_scene(args):
@@ -212,7 +256,9 @@ def run_ours(args):
                   "generate_ms": 0.0}
         start.record(stream)
         for k in range(args.steps):
+            t_host = time.perf_counter()
             st = step(k, e2e)
+            totals["host_ms"] = totals.get("host_ms", 0.0) + (time.perf_counter() - t_host) * 1e3
             totals["closest"] += st.closest_rays
             totals["shadow"] += st.shadow_rays
             totals["launches"] += st.kernel_launches + (1 if rank == 0 else 0)
@@ -235,7 +281,8 @@ def run_ours(args):
         return float(ms.item()), [float(x) for x in counts.tolist()], totals
 
     for k in range(args.warmup):
-        step(1000 + k, True)
+        step(1000 + k, False)  # both legs are warmed: the device-film leg (torch ops on the film load lazily) ...
+        step(2000 + k, True)   # ... and the host-film leg through cray_render
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -272,7 +319,7 @@ def run_ours(args):
                          "rays_in_kernel": totals["closest"], "kernel_ms": extend_ms, "kernel_share_of_step": extend_ms / max(totals["render_ms"], 1e-9),
                          "traffic": traffic},
             "stage_ms_per_step": {"extend": totals["trace_ms"] / args.steps, "shade": totals["shade_ms"] / args.steps, "shadow": totals["shadow_ms"] / args.steps,
-                                  "generate": totals["generate_ms"] / args.steps, "render_call": totals["render_ms"] / args.steps,
+                                  "generate": totals["generate_ms"] / args.steps, "render_call": totals["render_ms"] / args.steps, "host_step": totals["host_ms"] / args.steps,
                                   "iterations": totals["iters"] / args.steps},
             "clocks": clocks,
             "setup": {"parse_and_standin_s": parse_s, "bvh_build_ms": scene.info.bvh_build_ms, "upload_ms": scene.info.upload_ms, "scene_create_s": create_s,
