@@ -16,7 +16,7 @@ enum : uint32_t { PRIM_SPHERE = CRAY_SHAPE_SPHERE, PRIM_TRIANGLE = CRAY_SHAPE_TR
 struct alignas(16) LeafPrim {
     double d[9];
     uint32_t prim;   // index in reference primitive order
-    uint32_t kind;   // PRIM_* | shade class << 8 (k_shade groups paths by it) | disk index << 16
+    uint32_t kind;   // PRIM_* | shade class << 8 (k_shade groups paths by it) | disk: index << 16, triangle: kKindFlatTriangle
 };
 static_assert(sizeof(LeafPrim) == 80, "LeafPrim layout");
 
@@ -26,12 +26,17 @@ struct DiskXf {      // Shape::Disk, shape.rs:41-46
     double radius, inner_radius;
 };
 
-struct alignas(16) TriShade {  // shading attributes of Shape::Triangle, indexed by shape_index
-    double n0[3], n01[3], n02[3];
+// Shading attributes of a triangle primitive, indexed by PRIMITIVE index (slots of non-triangle primitives are unused).
+// The first 32-byte sector is all a flat-shaded, untextured triangle needs: its normal and what Primitive binds to it.
+struct alignas(32) TriShade {
+    double n0[3];
+    int32_t material;      // into SceneView::materials (the black matte for area lights, primitive.rs:43-46)
+    int32_t area_light;    // into SceneView::lights, or -1
+    double n01[3], n02[3];
     double uv0[2], uv01[2], uv02[2];
-    double _pad;
 };
 static_assert(sizeof(TriShade) == 128, "TriShade layout");
+constexpr uint32_t kKindFlatTriangle = 1u << 16;  // LeafPrim::kind flag: n01 and n02 are all +0.0 (no vertex normals)
 
 enum : uint32_t { LOBE_LAMBERTIAN = 0, LOBE_OREN_NAYAR = 1, LOBE_CONDUCTOR = 2, LOBE_SPECULAR_BRDF = 3, LOBE_SPECULAR_BTDF = 4, LOBE_FRESNEL_SPECULAR = 5 };
 

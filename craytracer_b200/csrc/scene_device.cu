@@ -48,6 +48,11 @@ LeafPrim make_leaf_prim(const cray_scene_desc& d, uint32_t prim) {
             std::memcpy(lp.d + 3, t.e1, 24);
             std::memcpy(lp.d + 6, t.e2, 24);
             lp.kind = PRIM_TRIANGLE;
+            {   // flat: every component of n01 and n02 is +0.0 bit for bit, so n0 + n01 * u + n02 * v == n0 + (+0.0) + (+0.0)
+                const double z[6] = {t.n01[0], t.n01[1], t.n01[2], t.n02[0], t.n02[1], t.n02[2]};
+                const uint64_t zero_bits[6] = {0, 0, 0, 0, 0, 0};
+                if (std::memcmp(z, zero_bits, sizeof(z)) == 0) lp.kind |= kKindFlatTriangle;
+            }
             break;
         }
         case CRAY_SHAPE_SPHERE: {
@@ -251,13 +256,27 @@ int cray_scene_create(const cray_scene_desc* d, int device, uint32_t build_flags
     }
     std::vector<DiskXf> disks(d->n_disks);
     for (size_t i = 0; i < disks.size(); ++i) disks[i] = make_disk(d->disks[i]);
-    std::vector<TriShade> tri_shade(d->n_triangles);
-    for (size_t i = 0; i < tri_shade.size(); ++i) {
-        const cray_triangle_desc& t = d->triangles[i];
-        TriShade& ts = tri_shade[i];
-        std::memcpy(ts.n0, t.n0, 24); std::memcpy(ts.n01, t.n01, 24); std::memcpy(ts.n02, t.n02, 24);
-        std::memcpy(ts.uv0, t.uv0, 16); std::memcpy(ts.uv01, t.uv01, 16); std::memcpy(ts.uv02, t.uv02, 16);
-        ts._pad = 0.0;
+    // per-primitive shading records for triangles (flat ones are flagged in their LeafPrim, see make_leaf_prim)
+    std::vector<TriShade> tri_shade(d->n_triangles ? np : 0);
+    {
+        const unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+        std::vector<std::thread> pool;
+        auto work = [&](unsigned t0) {
+            for (size_t i = t0; i < tri_shade.size(); i += nt) {
+                const cray_primitive_desc& p = d->primitives[i];
+                TriShade& ts = tri_shade[i];
+                std::memset(&ts, 0, sizeof(ts));
+                if (p.shape_kind != CRAY_SHAPE_TRIANGLE) continue;
+                const cray_triangle_desc& t = d->triangles[p.shape_index];
+                std::memcpy(ts.n0, t.n0, 24); std::memcpy(ts.n01, t.n01, 24); std::memcpy(ts.n02, t.n02, 24);
+                std::memcpy(ts.uv0, t.uv0, 16); std::memcpy(ts.uv01, t.uv01, 16); std::memcpy(ts.uv02, t.uv02, 16);
+                ts.material = p.area_light >= 0 ? (int32_t)d->n_materials : p.material;
+                ts.area_light = p.area_light;
+            }
+        };
+        for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (auto& th : pool) th.join();
     }
     // materials (+ the black matte that area-light primitives carry, primitive.rs:43-46)
     std::vector<DevMaterial> materials(d->n_materials + 1);

@@ -160,9 +160,14 @@ __device__ __forceinline__ void surface_at(const SceneView& s, const LeafPrim& l
     const uint32_t kind = lp.kind & 0xFFu;
     tex_u = 0.0; tex_v = 0.0;
     if (kind == PRIM_TRIANGLE) {  // shape.rs:249-258
-        const TriShade& ts = s.tri_shade[s.prims[lp.prim].shape_index];
+        const TriShade& ts = s.tri_shade[lp.prim];
         location = o + dir * t;
-        const V3 n0 = mk(ts.n0[0], ts.n0[1], ts.n0[2]), n01 = mk(ts.n01[0], ts.n01[1], ts.n01[2]), n02 = mk(ts.n02[0], ts.n02[1], ts.n02[2]);
+        const V3 n0 = mk(ts.n0[0], ts.n0[1], ts.n0[2]);
+        V3 n01 = mk(0.0, 0.0, 0.0), n02 = mk(0.0, 0.0, 0.0);
+        if (!(lp.kind & kKindFlatTriangle)) {  // flat triangles: both are +0.0, and the record's first sector is all that is read
+            n01 = mk(ts.n01[0], ts.n01[1], ts.n01[2]);
+            n02 = mk(ts.n02[0], ts.n02[1], ts.n02[2]);
+        }
         normal = normalized(n0 + n01 * bu + n02 * bv);
         if (want_uv) {
             tex_u = ts.uv0[0] + ts.uv01[0] * bu + ts.uv02[0] * bv;

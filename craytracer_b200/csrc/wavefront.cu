@@ -429,10 +429,16 @@ __global__ void __launch_bounds__(128) k_extend_exact(SceneView s, Pool p, const
 //
 // Paths of one block are first grouped by (shade class, shape kind) of what they hit -- a counting sort of the block's 256
 // queue entries in shared memory -- so that the lanes of a warp run the same material / surface code.
-constexpr uint32_t kShadeThreads = 256;
+#ifndef CRAY_SHADE_THREADS
+#define CRAY_SHADE_THREADS 256
+#endif
+#ifndef CRAY_SHADE_BLOCKS
+#define CRAY_SHADE_BLOCKS 3
+#endif
+constexpr uint32_t kShadeThreads = CRAY_SHADE_THREADS;
 constexpr uint32_t kShadeKeys = 16;   // class (matte, glass, plastic, metal) x shape kind (3); 12 = miss; 13 = no path
 
-__global__ void __launch_bounds__(kShadeThreads, 2) k_shade(SceneView s, Pool p, Job job, Counters* counters) {
+__global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(SceneView s, Pool p, Job job, Counters* counters) {
     constexpr uint32_t kWarps = kShadeThreads / 32, kCells = kShadeKeys * kWarps;  // 128 (key, warp) cells
     __shared__ uint32_t s_count[kCells];
     __shared__ uint32_t s_warp_total[kCells / 32];
@@ -524,22 +530,30 @@ __global__ void __launch_bounds__(kShadeThreads, 2) k_shade(SceneView s, Pool p,
         double t2;
         triangle_eval(lp.d, ro, rd, t2, bu, bv);
     }
-    const cray_primitive_desc prim = s.prims[lp.prim];
-    const DevMaterial& material = s.materials[prim.material];
+    // Primitive's material / light binding: triangles carry it in the first sector of their shading record
+    int32_t material_index, area_light;
+    if ((lp.kind & 0xFFu) == PRIM_TRIANGLE) {
+        const int2 ids = __ldg(reinterpret_cast<const int2*>(&s.tri_shade[lp.prim].material));
+        material_index = ids.x; area_light = ids.y;
+    } else {
+        const cray_primitive_desc prim = s.prims[lp.prim];
+        material_index = prim.material; area_light = prim.area_light;
+    }
+    const DevMaterial& material = s.materials[material_index];
     surface_at(s, lp, ro, rd, hit_t, bu, bv, location, normal, tu, tv, material.needs_uv != 0u);
 
     // PathSegmentSamples::from path_integrator.rs:25-36 -- dimensions 4 + 8 * bounces ... (evaluated where consumed)
     const VertexSamples vs{job.sobol, p.shuffled_rev[i], p.hash[i], 4u + 8u * bounces};
 
     // emission (:106-126)
-    if (prim.area_light >= 0) {
-        const DevLight& light = s.lights[prim.area_light];
+    if (area_light >= 0) {
+        const DevLight& light = s.lights[area_light];
         const Color3 Le = mkc(light.color[0], light.color[1], light.color[2]);
         if (!is_black(Le)) {
             if (is_specular_bounce) {
                 L = L + beta * Le;
             } else {
-                const double light_pdf = light_pdf_li(s, light, location, normal, w_o).value * light_pick_pdf(s, (uint32_t)prim.area_light);
+                const double light_pdf = light_pdf_li(s, light, location, normal, w_o).value * light_pick_pdf(s, (uint32_t)area_light);
                 const double weight = power_heuristic(light_pdf, prev_bsdf_pdf);
                 L = L + beta * Le * weight;
             }
