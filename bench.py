@@ -317,7 +317,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_wide_persistent<false, ExtendSource> (closest-hit traversal, 8-wide BVH)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_kind, "algorithmic_bytes_per_ray": ALGORITHMIC_BYTES_PER_RAY,
                          "rays_in_kernel": totals["closest"], "kernel_ms": extend_ms, "kernel_share_of_step": extend_ms / max(totals["render_ms"], 1e-9),
-                         "traffic": traffic},
+                         "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "traffic_detail": traffic},
             "stage_ms_per_step": {"extend": totals["trace_ms"] / args.steps, "shade": totals["shade_ms"] / args.steps, "shadow": totals["shadow_ms"] / args.steps,
                                   "generate": totals["generate_ms"] / args.steps, "render_call": totals["render_ms"] / args.steps, "host_step": totals["host_ms"] / args.steps,
                                   "iterations": totals["iters"] / args.steps},
