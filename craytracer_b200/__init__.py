@@ -16,7 +16,7 @@ from ._abi import (BUILD_EXACT, BUILD_FAST, CRAY_NO_HIT, HIT_DTYPE, RAY_DTYPE, S
                    SceneInfo)
 
 __all__ = ["ParserError", "CrayError", "HostScene", "Scene", "parse_scene", "load_scene", "make_rays", "tokenize", "parse_raw_value",
-           "register_standin_mesh", "TRAVERSE_EXACT", "TRAVERSE_FAST", "BUILD_EXACT", "BUILD_FAST", "CRAY_NO_HIT"]
+           "register_standin_mesh", "write_exr", "TRAVERSE_EXACT", "TRAVERSE_FAST", "BUILD_EXACT", "BUILD_FAST", "CRAY_NO_HIT"]
 
 
 class CrayError(RuntimeError):
@@ -138,6 +138,14 @@ def tokenize(text):
 def parse_raw_value(text):
     """RawValue::from_tokens(tokenize(input)) of src/scene_parser.rs:336."""
     return _json_call(_abi.lib().cray_debug_parse_raw_value, text)
+
+
+def write_exr(path, film):
+    """The EXR save of src/bin/craytracer.rs:367-369: (H, W, 3) f32 linear RGB -> 32-bit float OpenEXR."""
+    film = np.ascontiguousarray(film, dtype=np.float32)
+    h, w, ch = film.shape
+    assert ch == 3
+    _check(_abi.lib().cray_write_exr(os.fspath(path).encode(), w, h, film.ctypes.data))
 
 
 def make_rays(origins, directions, max_distance=np.inf):

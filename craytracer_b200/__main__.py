@@ -1,0 +1,81 @@
+"""Command line of the reference (src/bin/craytracer.rs:321-374) over the B200 path:
+
+    python -m craytracer_b200 --scene scenes/dragon.cry [--output out.exr] [--seed 0] [--spp N] [--mode fast|exact] [--gpus N]
+
+Same flags as the reference's `Cli` (--scene/-s, --output, --seed, --preview); --preview is accepted and ignored (no window:
+SURVEY section 2 marks the minifb preview out of scope).  Meshes named by a scene are resolved against the scene file's
+directory's parent, the current directory and this repository's assets/; meshes that exist nowhere (the reference does not
+ship xyzrgb_dragon.obj / staircase.obj) fall back to the documented procedural stand-ins with a warning.
+With --gpus N > 1 the sample range is split over N processes-free GPU contexts of this process (one scene per device) and the
+films are summed on the host; the multi-process NCCL path is bench.py's."""
+import argparse
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+from . import Scene, TRAVERSE_EXACT, TRAVERSE_FAST, load_scene, scenes, write_exr
+from .distributed import shard_samples
+
+
+def find_base_dir(scene_path):
+    """The reference resolves mesh paths against the process CWD (it is run from the repository root)."""
+    here = os.path.dirname(os.path.abspath(scene_path))
+    for cand in (os.getcwd(), os.path.dirname(here), here, scenes.ASSETS):
+        if os.path.isdir(os.path.join(cand, "objs")):
+            return cand
+    return scenes.ASSETS
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(prog="craytracer_b200", description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--scene", "-s", required=True, help=".cry scene file")
+    ap.add_argument("--output", default="out.exr")
+    ap.add_argument("--preview", action="store_true", help="accepted for compatibility; ignored")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--spp", type=int, default=None, help="override the scene's num_samples")
+    ap.add_argument("--mode", choices=["fast", "exact"], default="fast")
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--base-dir", default=None, help="directory mesh paths are resolved against")
+    args = ap.parse_args(argv)
+
+    start = time.time()
+    scenes.register_standins()
+    base = args.base_dir or find_base_dir(args.scene)
+    hs = load_scene(args.scene, base_dir=base)
+    for w in hs.warnings:
+        print(f"[WARN] {w}", file=sys.stderr)
+    devices = list(range(max(1, args.gpus)))
+    gpu_scenes = [Scene(hs, device=d) for d in devices]
+    print(f"[INFO] Scene constructed in {time.time() - start:.3f}s", file=sys.stderr)
+
+    sc0 = gpu_scenes[0]
+    spp = args.spp if args.spp is not None else sc0.num_samples
+    mode = TRAVERSE_EXACT if args.mode == "exact" else TRAVERSE_FAST
+    films, stats = [None] * len(devices), [None] * len(devices)
+
+    def work(k):
+        lo, hi = shard_samples(spp, k, len(devices))
+        films[k], stats[k] = gpu_scenes[k].render(seed=args.seed, sample_begin=lo, sample_end=hi, mode=mode)
+
+    t0 = time.time()
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(devices))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    film = np.sum(films, axis=0, dtype=np.float32) / np.float32(max(spp, 1))  # pixels /= num_samples (craytracer.rs:253-259)
+    dt = time.time() - t0
+    rays = sum(s.closest_rays + s.shadow_rays for s in stats)
+    dropped = sum(s.nan_samples for s in stats)
+    print(f"[INFO] Rendering finished in {dt:.3f}s ({rays / max(dt, 1e-9) / 1e6:.1f} Mrays/s, {sc0.width * sc0.height * spp / max(dt, 1e-9) / 1e6:.1f} Msamples/s"
+          + (f", {dropped} samples dropped where the reference would assert" if dropped else "") + ")", file=sys.stderr)
+    write_exr(args.output, film)
+    print(f"[INFO] Wrote {args.output}", file=sys.stderr)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -74,6 +74,59 @@ int cray_host_scene_load(const char* cry_path, const char* base_dir, cray_host_s
     return cray_host_scene_parse(ss.str().c_str(), base_dir, out);
 }
 
+// OpenEXR 2.0 single-part scan-line file, channels B, G, R as 32-bit float, NO_COMPRESSION, increasing-y line order.
+int cray_write_exr(const char* path, uint32_t width, uint32_t height, const float* rgb) {
+    if (!path || !rgb || width == 0 || height == 0) { cray::set_error("bad arguments"); return CRAY_E_INVALID; }
+    std::string head;
+    auto put = [&](const void* p, size_t n) { head.append(static_cast<const char*>(p), n); };
+    auto put_i32 = [&](int32_t v) { put(&v, 4); };
+    auto put_f32 = [&](float v) { put(&v, 4); };
+    auto put_str = [&](const char* z) { head.append(z); head.push_back('\0'); };
+    auto attr = [&](const char* name, const char* type, int32_t size) { put_str(name); put_str(type); put_i32(size); };
+    put_i32(20000630);  // magic
+    put_i32(2);         // version 2, no flags: single-part scan-line
+    attr("channels", "chlist", 3 * (2 + 4 + 4 + 4 + 4) + 1);
+    for (const char* ch : {"B", "G", "R"}) {
+        put_str(ch);
+        put_i32(2);  // FLOAT
+        put_i32(0);  // pLinear + 3 reserved bytes
+        put_i32(1); put_i32(1);  // x / y sampling
+    }
+    head.push_back('\0');
+    attr("compression", "compression", 1); head.push_back('\0');
+    attr("dataWindow", "box2i", 16); put_i32(0); put_i32(0); put_i32((int32_t)width - 1); put_i32((int32_t)height - 1);
+    attr("displayWindow", "box2i", 16); put_i32(0); put_i32(0); put_i32((int32_t)width - 1); put_i32((int32_t)height - 1);
+    attr("lineOrder", "lineOrder", 1); head.push_back('\0');
+    attr("pixelAspectRatio", "float", 4); put_f32(1.0f);
+    attr("screenWindowCenter", "v2f", 8); put_f32(0.0f); put_f32(0.0f);
+    attr("screenWindowWidth", "float", 4); put_f32(1.0f);
+    head.push_back('\0');  // end of header
+    const uint64_t row_bytes = (uint64_t)width * 3 * 4, chunk = 8 + row_bytes;
+    const uint64_t first = head.size() + 8ull * height;
+    std::ofstream f(path, std::ios::binary);
+    if (!f) { cray::set_error(std::string("cannot open ") + path + " for writing"); return CRAY_E_IO; }
+    f.write(head.data(), (std::streamsize)head.size());
+    for (uint32_t y = 0; y < height; ++y) {
+        const uint64_t off = first + chunk * y;
+        f.write(reinterpret_cast<const char*>(&off), 8);
+    }
+    std::vector<float> line((size_t)width * 3);
+    for (uint32_t y = 0; y < height; ++y) {
+        const int32_t yy = (int32_t)y, size = (int32_t)row_bytes;
+        f.write(reinterpret_cast<const char*>(&yy), 4);
+        f.write(reinterpret_cast<const char*>(&size), 4);
+        const float* src = rgb + (size_t)y * width * 3;
+        for (uint32_t x = 0; x < width; ++x) {  // channel-planar within a scan line, channels in alphabetical order
+            line[x] = src[3 * x + 2];
+            line[width + x] = src[3 * x + 1];
+            line[2 * (size_t)width + x] = src[3 * x];
+        }
+        f.write(reinterpret_cast<const char*>(line.data()), (std::streamsize)row_bytes);
+    }
+    if (!f) { cray::set_error(std::string("error writing ") + path); return CRAY_E_IO; }
+    return CRAY_OK;
+}
+
 const cray_scene_desc* cray_host_scene_desc(const cray_host_scene* hs) { return hs ? &hs->scene->desc : nullptr; }
 
 void cray_host_scene_destroy(cray_host_scene* hs) {

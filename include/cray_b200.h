@@ -211,6 +211,12 @@ int cray_render(cray_scene*, int mode, uint64_t seed, uint32_t sample_begin, uin
 int cray_render_device(cray_scene*, int mode, uint64_t seed, uint32_t sample_begin, uint32_t sample_end,
                        float* d_rgb_sum, void* stream, cray_render_stats* stats);
 
+/* ---- output (the EXR save of src/bin/craytracer.rs:367-369) ----------------------- */
+
+/* Writes `rgb` (W*H*3 f32, row-major, linear RGB -- what render() hands to on_render_finish) as an OpenEXR file with three
+ * 32-bit float channels (the reference's `write_rgb_file`, exr crate): single-part scan-line image, no compression. */
+int cray_write_exr(const char* path, uint32_t width, uint32_t height, const float* rgb);
+
 /* ---- introspection ------------------------------------------------------------- */
 
 typedef struct cray_scene_info {
