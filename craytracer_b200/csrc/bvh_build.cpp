@@ -3,7 +3,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -49,9 +52,26 @@ struct Task {
     SubTree tree;
 };
 
+// Runs fn(chunk, begin, end) over [0, n) split into `threads` contiguous chunks, one thread each.
+template <class F>
+void parallel_chunks(size_t n, unsigned threads, F fn) {
+    threads = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, n));
+    const size_t step = (n + threads - 1) / threads;
+    std::vector<std::thread> pool;
+    for (unsigned c = 1; c < threads; ++c) {
+        const size_t b = std::min(n, c * step), e = std::min(n, b + step);
+        pool.emplace_back([=] { fn(c, b, e); });
+    }
+    fn(0u, (size_t)0, std::min(n, step));
+    for (auto& th : pool) th.join();
+}
+
+constexpr size_t kParallelNode = 1u << 15;  // nodes with at least this many primitives are split by all threads
+
 struct Builder {
     size_t grain;                 // subtrees at or below this size are deferred to the pool (0 = never defer)
     std::vector<Task>* tasks;
+    unsigned threads = 1;         // > 1: the passes over the items of a large node run on this many threads
 
     uint32_t leaf(SubTree& t, const Item* items, size_t n, const Box3& box) {
         uint32_t idx = (uint32_t)t.nodes.size();
@@ -68,11 +88,29 @@ struct Builder {
             t.nodes.push_back({Box3{}, (uint32_t)tasks->size() - 1, 0u, kDeferred, 0u});
             return idx;
         }
+        // Every reduction of this function is a min / max or a count, so chunking it over threads changes no bit of the tree.
+        const bool parallel = threads > 1 && n >= kParallelNode;
         Accum all, cent;
-        for (size_t i = 0; i < n; ++i) {
-            all.add(items[i].lo, items[i].hi);
-            double c[3] = {centroid_axis(items[i], 0), centroid_axis(items[i], 1), centroid_axis(items[i], 2)};
-            cent.add(c, c);
+        auto accumulate = [&](Accum& a, Accum& c3, size_t b, size_t e) {
+            for (size_t i = b; i < e; ++i) {
+                a.add(items[i].lo, items[i].hi);
+                double c[3] = {centroid_axis(items[i], 0), centroid_axis(items[i], 1), centroid_axis(items[i], 2)};
+                c3.add(c, c);
+            }
+        };
+        if (parallel) {
+            std::vector<Accum> pa(threads), pc(threads);
+            parallel_chunks(n, threads, [&](unsigned c, size_t b, size_t e) {
+                Accum a, c3;  // thread-local: neighbouring slots of pa / pc share cache lines
+                accumulate(a, c3, b, e);
+                pa[c] = a; pc[c] = c3;
+            });
+            for (unsigned c = 0; c < threads; ++c) {
+                if (pa[c].some) all.add(pa[c].lo, pa[c].hi);
+                if (pc[c].some) cent.add(pc[c].lo, pc[c].hi);
+            }
+        } else {
+            accumulate(all, cent, 0, n);
         }
         const Box3 bounds = all.box();
         if (n <= 1) return leaf(t, items, n, bounds);
@@ -86,16 +124,38 @@ struct Builder {
         const int axis = box_maximum_extent(cb);
         const double cmin = cb.lo[axis], cext = cb.hi[axis] - cb.lo[axis];
 
-        Accum bucket_box[kBuckets];
-        size_t bucket_count[kBuckets] = {};
-        for (size_t i = 0; i < n; ++i) {
-            const double offset = (centroid_axis(items[i], axis) - cmin) / cext;                 // Bounds::offset bounds.rs:55-61
-            const uint64_t raw = as_usize((double)kBuckets * offset);                             // `as usize`, NaN -> 0
-            const uint32_t b = (uint32_t)std::min<uint64_t>(raw, kBuckets - 1);
-            items[i].bucket = b;
-            bucket_box[b].add(items[i].lo, items[i].hi);
-            bucket_count[b] += 1;
+        struct Buckets {
+            Accum box[kBuckets];
+            size_t count[kBuckets] = {};
+        };
+        Buckets bk;
+        auto fill = [&](Buckets& dst, size_t b0, size_t e0) {
+            for (size_t i = b0; i < e0; ++i) {
+                const double offset = (centroid_axis(items[i], axis) - cmin) / cext;                 // Bounds::offset bounds.rs:55-61
+                const uint64_t raw = as_usize((double)kBuckets * offset);                             // `as usize`, NaN -> 0
+                const uint32_t b = (uint32_t)std::min<uint64_t>(raw, kBuckets - 1);
+                items[i].bucket = b;
+                dst.box[b].add(items[i].lo, items[i].hi);
+                dst.count[b] += 1;
+            }
+        };
+        if (parallel) {
+            std::vector<Buckets> part(threads);
+            parallel_chunks(n, threads, [&](unsigned c, size_t b0, size_t e0) {
+                Buckets local;
+                fill(local, b0, e0);
+                part[c] = local;
+            });
+            for (unsigned c = 0; c < threads; ++c)
+                for (uint32_t b = 0; b < kBuckets; ++b) {
+                    if (part[c].box[b].some) bk.box[b].add(part[c].box[b].lo, part[c].box[b].hi);
+                    bk.count[b] += part[c].count[b];
+                }
+        } else {
+            fill(bk, 0, n);
         }
+        Accum* bucket_box = bk.box;
+        size_t* bucket_count = bk.count;
         double costs[kBuckets - 1];
         for (uint32_t i = 0; i + 1 < kBuckets; ++i) {
             double cost = kTraversalCost;
@@ -117,13 +177,48 @@ struct Builder {
         if ((double)n <= costs[best] && n <= kMaxLeaf) return leaf(t, items, n, bounds);
 
         // partition_by util.rs:4-26 with pred = bucket <= best
-        size_t left = 0, right = n - 1;
-        while (left != right) {
-            while (left < right && items[left].bucket <= best) left += 1;
-            while (right > left && !(items[right].bucket <= best)) right -= 1;
-            std::swap(items[left], items[right]);
+        size_t mid;
+        if (parallel) {
+            // The sequential two-pointer loop never moves an item that already sits on its side; it swaps the k-th item that
+            // fails the predicate inside the first m positions (ascending) with the k-th item that passes it behind them
+            // (descending), m = number of passing items.  The same pairs, found with per-chunk counts and swapped in parallel:
+            size_t m = 0;
+            for (uint32_t b = 0; b <= best; ++b) m += bucket_count[b];
+            std::vector<size_t> nf(threads + 1, 0), nt(threads + 1, 0);
+            parallel_chunks(n, threads, [&](unsigned c, size_t b0, size_t e0) {
+                size_t f = 0, tr = 0;
+                for (size_t i = b0; i < e0; ++i) {
+                    const bool pass = items[i].bucket <= best;
+                    if (i < m) f += !pass;
+                    else tr += pass;
+                }
+                nf[c + 1] = f; nt[c + 1] = tr;
+            });
+            for (unsigned c = 0; c < threads; ++c) { nf[c + 1] += nf[c]; nt[c + 1] += nt[c]; }
+            const size_t k = nf[threads];
+            std::vector<uint32_t> fpos(k), tpos(k);
+            parallel_chunks(n, threads, [&](unsigned c, size_t b0, size_t e0) {
+                size_t f = nf[c], tr = nt[c];
+                for (size_t i = b0; i < e0; ++i) {
+                    const bool pass = items[i].bucket <= best;
+                    if (i < m) { if (!pass) fpos[f++] = (uint32_t)i; }
+                    else if (pass) tpos[tr++] = (uint32_t)i;
+                }
+            });
+            if (nt[threads] == k)
+                parallel_chunks(k, threads, [&](unsigned, size_t b0, size_t e0) {
+                    for (size_t j = b0; j < e0; ++j) std::swap(items[fpos[j]], items[tpos[k - 1 - j]]);
+                });
+            mid = m;
+        } else {
+            size_t left = 0, right = n - 1;
+            while (left != right) {
+                while (left < right && items[left].bucket <= best) left += 1;
+                while (right > left && !(items[right].bucket <= best)) right -= 1;
+                std::swap(items[left], items[right]);
+            }
+            mid = items[left].bucket <= best ? left + 1 : left;
         }
-        const size_t mid = items[left].bucket <= best ? left + 1 : left;
         if (mid == 0 || mid == n) {
             if (t.error.empty()) t.error = "SAH split left one side empty (the reference asserts, bvh.rs:327-328)";
             return leaf(t, items, n, bounds);
@@ -218,6 +313,7 @@ Box3 primitive_bounds(const cray_scene_desc& d, uint64_t prim) {  // Shape::boun
 }
 
 void build_reference_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads) {
+    PhaseTimer timer;
     const size_t n = (size_t)d.n_primitives;
     out = RefBvh{};
     if (n == 0) { out.error = "no primitives"; return; }
@@ -240,18 +336,21 @@ void build_reference_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads
         work(0, std::min(n, chunk));
         for (auto& th : pool) th.join();
     }
+    timer.mark("primitive bounds");
     Accum all;
     for (size_t i = 0; i < n; ++i) all.add(items[i].lo, items[i].hi);
     out.bounds = all.box();  // Bvh::bounds bvh.rs:53
+    timer.mark("scene bounds");
 
     std::vector<Task> tasks;
     SubTree top;
-    Builder top_builder{(threads > 1 && n > (1u << 16)) ? std::max<size_t>(1u << 14, n / (threads * 16)) : 0, &tasks};
+    Builder top_builder{(threads > 1 && n > (1u << 16)) ? std::max<size_t>(1u << 15, n / (threads * 8)) : 0, &tasks, threads};
     top_builder.split(top, items.data(), n);
+    timer.mark("top of the tree");
     if (!tasks.empty()) {
         std::atomic<size_t> next{0};
         auto run = [&]() {
-            Builder b{0, nullptr};
+            Builder b{0, nullptr, 1};
             for (;;) {
                 size_t i = next.fetch_add(1);
                 if (i >= tasks.size()) break;
@@ -263,10 +362,14 @@ void build_reference_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads
         run();
         for (auto& th : pool) th.join();
     }
-    out.nodes.reserve(2 * n / 3 + 16);
+    timer.mark("sub-trees");
+    size_t total_nodes = top.nodes.size();
+    for (const Task& t : tasks) total_nodes += t.tree.nodes.size();
+    out.nodes.reserve(total_nodes);
     out.prim_order.reserve(n);
     out.error = top.error;
     splice(top, tasks, out);
+    timer.mark("splice");
 }
 
 // ---- 8-wide collapse ----------------------------------------------------------------------------------
@@ -309,7 +412,6 @@ struct Collapser {
     const cray_scene_desc& desc;
     const RefBvh& ref;
     WideBvh& out;
-    uint32_t max_depth = 0;
     std::vector<DpNode> dp;          // [0, ref.nodes.size()): the reference nodes; then the virtual nodes inside multi-primitive leaves
     std::vector<Box3> virtual_box;   // boxes of the virtual nodes
 
@@ -391,7 +493,43 @@ struct Collapser {
         collect(n.right, i - k, kids);
     }
 
-    void expand(uint32_t wide_idx, uint32_t r, uint32_t depth) {
+    // Wide nodes (not counting r's own) and primitives the subtree of wide node r occupies: integers from the DP decisions only.
+    struct Extent { uint64_t nodes, prims; };
+    void count_slots(uint32_t r, int i, Extent& e) const {
+        if (r & kPrimRef) { e.prims += 1; return; }
+        const DpNode& n = dp[r];
+        while (i >= 2 && (n.split[i - 2] & 0x80u)) i -= 1;
+        if (i == 1) { e.nodes += 1; count_node(r, e); return; }
+        const int k = n.split[i - 2] & 7;
+        count_slots(n.left, k, e);
+        count_slots(n.right, i - k, e);
+    }
+    void count_node(uint32_t r, Extent& e) const {
+        if (r & kPrimRef) { e.prims += 1; return; }
+        const DpNode& n = dp[r];
+        const int k = n.split[6] & 7;
+        count_slots(n.left, k, e);
+        count_slots(n.right, 8 - k, e);
+    }
+
+    // Layout = depth-first: a node's primitives and its block of interior children are placed when the node is visited, then
+    // each child's subtree follows in order.  A subtree therefore owns one contiguous range of nodes and of primitives, and
+    // subtrees below kTaskDepth are written by a thread pool into ranges reserved from their extents -- the result is the
+    // array a single thread would have produced.
+    struct Cursor { uint32_t node, prim; };
+    struct EmitTask { uint32_t wide_idx, ref, depth; Cursor cursor; };
+    static constexpr uint32_t kTaskDepth = 3;
+    std::vector<EmitTask>* emit_tasks = nullptr;  // non-null while the top of the tree is laid out
+
+    void expand(uint32_t wide_idx, uint32_t r, uint32_t depth, Cursor& cur, uint32_t& deepest) {
+        if (emit_tasks && depth > kTaskDepth && !(r & kPrimRef)) {
+            Extent e{0, 0};
+            count_node(r, e);
+            emit_tasks->push_back({wide_idx, r, depth, cur});
+            cur.node += (uint32_t)e.nodes;
+            cur.prim += (uint32_t)e.prims;
+            return;
+        }
         std::vector<Kid> kids;
         if (r & kPrimRef) kids.push_back({r, box_of(r)});  // a scene of one primitive
         else {
@@ -400,11 +538,11 @@ struct Collapser {
             collect(n.left, k, kids);
             collect(n.right, 8 - k, kids);
         }
-        emit(wide_idx, kids, box_of(r), depth);
+        emit(wide_idx, kids, box_of(r), depth, cur, deepest);
     }
 
-    void emit(uint32_t wide_idx, const std::vector<Kid>& kids, const Box3& node_box, uint32_t depth) {
-        max_depth = std::max(max_depth, depth);
+    void emit(uint32_t wide_idx, const std::vector<Kid>& kids, const Box3& node_box, uint32_t depth, Cursor& cur, uint32_t& deepest) {
+        deepest = std::max(deepest, depth);
         const int k = (int)kids.size();
         // slot assignment: slot bits (x=4, y=2, z=1) set = child sits on the + side of the node centre on that axis
         const V3 nc = box_centroid(node_box);
@@ -446,7 +584,7 @@ struct Collapser {
             scale[ax] = std::ldexp(1.0, ex);
         }
         w.ex = (uint8_t)(e[0] + 127); w.ey = (uint8_t)(e[1] + 127); w.ez = (uint8_t)(e[2] + 127);
-        w.prim_base = (uint32_t)out.prim_order.size();
+        w.prim_base = cur.prim;
         std::vector<uint32_t> interior_kids;
         for (int s = 0; s < 8; ++s) {
             const int c = child_in[s];
@@ -464,17 +602,17 @@ struct Collapser {
             }
             if (kid.ref & kPrimRef) {
                 w.leafmask |= (uint8_t)(1u << s);
-                out.prim_order.push_back(kid.ref & ~kPrimRef);
+                out.prim_order[cur.prim++] = kid.ref & ~kPrimRef;
             } else {
                 w.imask |= (uint8_t)(1u << s);
                 interior_kids.push_back(kid.ref);
             }
         }
-        w.child_base = (uint32_t)out.nodes.size();
+        w.child_base = cur.node;
         out.nodes[wide_idx] = w;
-        const uint32_t base = (uint32_t)out.nodes.size();
-        out.nodes.resize(out.nodes.size() + interior_kids.size());
-        for (size_t i = 0; i < interior_kids.size(); ++i) expand(base + (uint32_t)i, interior_kids[i], depth + 1);
+        const uint32_t base = cur.node;
+        cur.node += (uint32_t)interior_kids.size();
+        for (size_t i = 0; i < interior_kids.size(); ++i) expand(base + (uint32_t)i, interior_kids[i], depth + 1, cur, deepest);
     }
 };
 
@@ -482,13 +620,41 @@ struct Collapser {
 
 void collapse_to_wide(const cray_scene_desc& d, const RefBvh& ref, WideBvh& out) {
     out = WideBvh{};
-    out.nodes.reserve(ref.prim_order.size() / 5 + 16);
-    out.prim_order.reserve(ref.prim_order.size());
-    out.nodes.resize(1);
+    PhaseTimer timer;
     Collapser c{d, ref, out};
     c.run_dp();
-    c.expand(0, c.ref_of_child(0), 1);
-    out.depth = c.max_depth;
+    timer.mark("collapse: dynamic programme");
+    const uint32_t root = c.ref_of_child(0);
+    Collapser::Extent total{1, 0};
+    c.count_node(root, total);
+    out.nodes.resize(total.nodes);
+    out.prim_order.resize(total.prims);
+    // the top of the tree on this thread, handing out the ranges of the subtrees below it ...
+    std::vector<Collapser::EmitTask> tasks;
+    c.emit_tasks = &tasks;
+    Collapser::Cursor cur{1, 0};
+    uint32_t deepest = 0;
+    c.expand(0, root, 1, cur, deepest);
+    c.emit_tasks = nullptr;
+    // ... and the subtrees on all threads
+    const unsigned threads = std::max(1u, std::thread::hardware_concurrency());
+    std::vector<uint32_t> task_depth(tasks.size(), 0);
+    std::atomic<size_t> next{0};
+    auto run = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= tasks.size()) break;
+            Collapser::Cursor local = tasks[i].cursor;
+            c.expand(tasks[i].wide_idx, tasks[i].ref, tasks[i].depth, local, task_depth[i]);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < threads && t < tasks.size(); ++t) pool.emplace_back(run);
+    run();
+    for (auto& th : pool) th.join();
+    for (uint32_t dd : task_depth) deepest = std::max(deepest, dd);
+    out.depth = deepest;
+    timer.mark("collapse: emit");
 }
 
 }  // namespace cray

@@ -9,13 +9,27 @@
 //    the binary tree are opened too: a leaf slot of a wide node holds exactly ONE primitive with its own
 //    quantised box, so the f64 primitive test only runs on primitives whose own box the ray enters.
 #pragma once
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "../../include/cray_b200.h"
 #include "cray_math.cuh"
 
 namespace cray {
+
+struct PhaseTimer {  // CRAY_BUILD_TIMING=1 prints where scene construction spends its time
+    bool on = std::getenv("CRAY_BUILD_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void mark(const char* what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[cray build] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
 
 struct BinNode {       // 64 B, uploaded as-is for the exact traversal mode
     Box3 box;          // f64 bounds, bit-identical to the reference's node bounds

@@ -236,6 +236,7 @@ int cray_scene_create(const cray_scene_desc* d, int device, uint32_t build_flags
     struct Guard { cray_scene* s; ~Guard() { if (s) cray_scene_destroy(s); } } guard{sc};
     CRAY_CUDA(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
 
+    PhaseTimer timer;
     const size_t np = (size_t)d->n_primitives;
     // leaf-ordered intersection records
     std::vector<LeafPrim> bin_prims(np), wide_prims(wide.prim_order.size());
@@ -254,6 +255,7 @@ int cray_scene_create(const cray_scene_desc* d, int device, uint32_t build_flags
         work(0);
         for (auto& th : pool) th.join();
     }
+    timer.mark("leaf records");
     std::vector<DiskXf> disks(d->n_disks);
     for (size_t i = 0; i < disks.size(); ++i) disks[i] = make_disk(d->disks[i]);
     // per-primitive shading records for triangles (flat ones are flagged in their LeafPrim, see make_leaf_prim)
@@ -278,6 +280,7 @@ int cray_scene_create(const cray_scene_desc* d, int device, uint32_t build_flags
         work(0);
         for (auto& th : pool) th.join();
     }
+    timer.mark("shading records");
     // materials (+ the black matte that area-light primitives carry, primitive.rs:43-46)
     std::vector<DevMaterial> materials(d->n_materials + 1);
     for (size_t i = 0; i < d->n_materials; ++i) materials[i] = make_material(d->materials[i]);
@@ -366,6 +369,7 @@ int cray_scene_create(const cray_scene_desc* d, int device, uint32_t build_flags
             }
 #endif
 
+    timer.mark("materials, lights, camera");
     SceneView& v = sc->view;
     const uint32_t* d_order = nullptr;
     const uint32_t* d_sobol = nullptr;
@@ -396,6 +400,7 @@ int cray_scene_create(const cray_scene_desc* d, int device, uint32_t build_flags
     v.camera = cam;
     v.bounds = ref.bounds;
     CRAY_CUDA(cudaDeviceSynchronize());
+    timer.mark("upload");
 
     cray_scene_info& info = sc->info;
     info.n_primitives = np;

@@ -1,0 +1,19 @@
+#!/usr/bin/env python3
+"""Scene construction phases on the bench workload (host threads of the GPU box): CRAY_BUILD_TIMING=1 python tools/build_timing.py"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import craytracer_b200 as c  # noqa: E402
+from craytracer_b200 import scenes  # noqa: E402
+
+os.environ.setdefault("CRAY_BUILD_TIMING", "1")
+scenes.register_standins()
+t = time.time()
+hs = c.parse_scene(scenes.dragon(), base_dir=os.path.join(ROOT, "assets"))
+print(f"parse + stand-in mesh {time.time() - t:.2f} s, host threads {os.cpu_count()}")
+t = time.time()
+scene = c.Scene(hs)
+print(f"cray_scene_create {time.time() - t:.2f} s (build {scene.info.bvh_build_ms:.0f} ms, upload {scene.info.upload_ms:.0f} ms)")
