@@ -131,6 +131,18 @@ __device__ __forceinline__ bool leaf_prim_any(const SceneView& s, const LeafPrim
     return disk_hit(s.disks[lp.kind >> 16], o, dir, ray_max, t, a, b, c);
 }
 
+// Spheres and disks of the wide-BVH closest-hit test below.  Out of line: scenes have a handful of them, and inlined their f64
+// transforms would set the register allocation of the whole traversal kernel.
+__device__ __noinline__ int analytic_candidate(const SceneView& s, const LeafPrim& lp, V3 o, V3 dir, double& ray_max, bool have_hit) {
+    double cand = ray_max, u, v;
+    if (leaf_prim_closest(s, lp, o, dir, cand, u, v)) { ray_max = cand; return 1; }
+    if (have_hit) {  // analytic shapes are few: re-evaluate against the next f64 above ray_max to detect a tie
+        double tie = __longlong_as_double(__double_as_longlong(ray_max) + 1);
+        if (leaf_prim_closest(s, lp, o, dir, tie, u, v) && tie == ray_max) return 2;
+    }
+    return 0;
+}
+
 // Wide-BVH closest-hit flavour.  0: rejected; 1: accepted (ray_max shrinks); 2: exact tie -- the strict `<` of
 // ray.rs:26 rejects it against the current ray_max, but its distance is bit-equal to it, so the reference keeps
 // whichever of the two primitives its own traversal reaches first.
@@ -143,13 +155,7 @@ __device__ __forceinline__ int leaf_prim_candidate(const SceneView& s, const Lea
         if (have_hit && t == ray_max) { u = tu; v = tv; return 2; }
         return 0;
     }
-    double cand = ray_max;
-    if (leaf_prim_closest(s, lp, o, dir, cand, u, v)) { ray_max = cand; return 1; }
-    if (have_hit) {  // analytic shapes are few: re-evaluate against the next f64 above ray_max to detect a tie
-        double tie = __longlong_as_double(__double_as_longlong(ray_max) + 1);
-        if (leaf_prim_closest(s, lp, o, dir, tie, u, v) && tie == ray_max) return 2;
-    }
-    return 0;
+    return analytic_candidate(s, lp, o, dir, ray_max, have_hit);
 }
 
 // The rest of PrimitiveIntersection (location, normal, uv) for an accepted hit at distance t.  `want_uv` = false skips the

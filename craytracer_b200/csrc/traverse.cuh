@@ -122,6 +122,21 @@ __device__ __forceinline__ float byte_to_float_k(uint32_t word, uint32_t sel) {
     return __uint_as_float(__byte_perm(word, 0x47000000u, 0x7604u | (sel << 4)));
 }
 
+#ifndef CRAY_FFMA2
+#define CRAY_FFMA2 1   // 0: scalar FFMA slab test (tuning builds)
+#endif
+// d = a * b + c on two f32 lanes at once (sm_100: fma.rn.f32x2, SASS FFMA2); each lane rounds exactly like fmaf
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+
 struct AxisPlanes {
     float A, Bn, Bf;
 };
@@ -193,6 +208,27 @@ __device__ __forceinline__ void node_step(const SceneView& s, WarpShared& ws, un
     const uint32_t fz0 = negz ? (uint32_t)n3.x : (uint32_t)n4.z, fz1 = negz ? (uint32_t)n3.y : (uint32_t)n4.w;
 
     uint32_t hits = 0;
+#if CRAY_FFMA2
+    // two slots per packed FFMA2 (sm_100 fma.rn.f32x2): half the FMA issue slots of the scalar loop
+    const float2 XA = make_float2(X.A, X.A), XBn = make_float2(X.Bn, X.Bn), XBf = make_float2(X.Bf, X.Bf);
+    const float2 YA = make_float2(Y.A, Y.A), YBn = make_float2(Y.Bn, Y.Bn), YBf = make_float2(Y.Bf, Y.Bf);
+    const float2 ZA = make_float2(Z.A, Z.A), ZBn = make_float2(Z.Bn, Z.Bn), ZBf = make_float2(Z.Bf, Z.Bf);
+#pragma unroll
+    for (int sl = 0; sl < 8; sl += 2) {
+        const uint32_t s0 = sl & 3, s1 = (sl + 1) & 3;
+        const float2 tnx = fma2(make_float2(byte_to_float_k(sl < 4 ? nx0 : nx1, s0), byte_to_float_k(sl < 4 ? nx0 : nx1, s1)), XA, XBn);
+        const float2 tny = fma2(make_float2(byte_to_float_k(sl < 4 ? ny0 : ny1, s0), byte_to_float_k(sl < 4 ? ny0 : ny1, s1)), YA, YBn);
+        const float2 tnz = fma2(make_float2(byte_to_float_k(sl < 4 ? nz0 : nz1, s0), byte_to_float_k(sl < 4 ? nz0 : nz1, s1)), ZA, ZBn);
+        const float2 tfx = fma2(make_float2(byte_to_float_k(sl < 4 ? fx0 : fx1, s0), byte_to_float_k(sl < 4 ? fx0 : fx1, s1)), XA, XBf);
+        const float2 tfy = fma2(make_float2(byte_to_float_k(sl < 4 ? fy0 : fy1, s0), byte_to_float_k(sl < 4 ? fy0 : fy1, s1)), YA, YBf);
+        const float2 tfz = fma2(make_float2(byte_to_float_k(sl < 4 ? fz0 : fz1, s0), byte_to_float_k(sl < 4 ? fz0 : fz1, s1)), ZA, ZBf);
+        const float tn0 = fmaxf(fmaxf(tnx.x, tny.x), fmaxf(tnz.x, 0.0f)), tn1 = fmaxf(fmaxf(tnx.y, tny.y), fmaxf(tnz.y, 0.0f));
+        const float tf0 = fminf(fminf(fminf(tfx.x, tfy.x), tfz.x) * kSlabSlack, r.tmax);
+        const float tf1 = fminf(fminf(fminf(tfx.y, tfy.y), tfz.y) * kSlabSlack, r.tmax);
+        hits |= (tn0 <= tf0 ? 1u : 0u) << sl;
+        hits |= (tn1 <= tf1 ? 1u : 0u) << (sl + 1);
+    }
+#else
 #pragma unroll
     for (int sl = 0; sl < 8; ++sl) {
         const uint32_t sel = sl & 3;
@@ -206,6 +242,7 @@ __device__ __forceinline__ void node_step(const SceneView& s, WarpShared& ws, un
         const float tf = fminf(fminf(fminf(tfx, tfy), tfz) * kSlabSlack, r.tmax);
         hits |= (tn <= tf ? 1u : 0u) << sl;
     }
+#endif
     // interior children: bit of slot sl moves to position sl ^ octinv (nearest child in the highest bit)
     uint32_t ih = hits & imask;
     if (r.octinv & 1u) ih = ((ih & 0x55u) << 1) | ((ih & 0xAAu) >> 1);
@@ -240,17 +277,14 @@ __device__ __forceinline__ void prim_round_closest(const SceneView& s, WarpShare
     const uint32_t owner = e >> kSlotBits, slot = e & kSlotMask;
     int verdict = 0;
     double t = 0.0;
-    uint32_t my_prim = 0;
-    V3 dir = mk(0.0, 0.0, 0.0);
     if (act) {
         const LeafPrim lp = load_leaf_prim(s.wide_prims + slot);
         const V3 o = mk(ws.ox[owner], ws.oy[owner], ws.oz[owner]);
-        dir = mk(ws.dx[owner], ws.dy[owner], ws.dz[owner]);
+        const V3 dir = mk(ws.dx[owner], ws.dy[owner], ws.dz[owner]);
         const double rmax = ws.tmax[owner];
         double cand = rmax, u, v;
         verdict = leaf_prim_candidate(s, lp, o, dir, cand, ws.best[owner] != CRAY_NO_HIT, u, v);
         t = verdict == 1 ? cand : rmax;
-        my_prim = lp.prim;
     }
     // accepted distances are positive f64: they order like their bit patterns, so one shared-memory atomicMin per
     // accepting lane leaves the ray's new closest distance in ws.tmax (a verdict-2 lane's t IS the current value)
@@ -274,9 +308,10 @@ __device__ __forceinline__ void prim_round_closest(const SceneView& s, WarpShare
             // the first verdict-1 winner of a group displaces the (farther) previous best; everyone else is compared with
             // the primitive currently holding this distance
             bool take = verdict == 1 && lane == (unsigned)(__ffs(wins) - 1);
-            if (!take) {
+            if (!take) {  // (the rare path re-reads what it needs instead of keeping it in registers through every round)
                 const uint32_t cur = ws.best[owner];
-                take = cur != slot && reference_visits_first(s, s.rank_of_prim[my_prim], s.rank_of_prim[s.wide_prims[cur].prim], dir);
+                const V3 dir = mk(ws.dx[owner], ws.dy[owner], ws.dz[owner]);
+                take = cur != slot && reference_visits_first(s, s.rank_of_prim[s.wide_prims[slot].prim], s.rank_of_prim[s.wide_prims[cur].prim], dir);
             }
             if (take) ws.best[owner] = slot;
             ws.tmax32[owner] = slab_tmax(t);

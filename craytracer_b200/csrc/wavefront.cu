@@ -174,7 +174,11 @@ struct WideTuning {
 #ifndef CRAY_WIDE_MIN_BLOCKS
 #define CRAY_WIDE_MIN_BLOCKS 5
 #endif
-constexpr int kWideMinBlocks = CRAY_WIDE_MIN_BLOCKS;   // CTAs of 128 threads per SM the register allocation is held to
+constexpr int kWideMinBlocks = CRAY_WIDE_MIN_BLOCKS;
+#ifndef CRAY_WIDE_MIN_BLOCKS_ANY
+#define CRAY_WIDE_MIN_BLOCKS_ANY 8
+#endif
+constexpr int kWideMinBlocksAny = CRAY_WIDE_MIN_BLOCKS_ANY;   // the any-hit instantiation carries less state   // CTAs of 128 threads per SM the register allocation is held to
 
 enum : int { LANE_IDLE = 0, LANE_LIVE = 1, LANE_DRAIN = 2 };
 
@@ -192,7 +196,7 @@ __device__ unsigned long long g_wide_stats[2][8];
 #endif
 
 template <bool ANY, class Source>
-__global__ void __launch_bounds__(128, kWideMinBlocks) k_wide_persistent(SceneView s, Source src, const unsigned long long* __restrict__ n_ptr, unsigned long long* cursor, WideTuning tune) {
+__global__ void __launch_bounds__(128, ANY ? kWideMinBlocksAny : kWideMinBlocks) k_wide_persistent(SceneView s, Source src, const unsigned long long* __restrict__ n_ptr, unsigned long long* cursor, WideTuning tune) {
     __shared__ WarpShared shared[4];
     WarpShared& ws = shared[threadIdx.x >> 5];
     const unsigned FULL = 0xFFFFFFFFu;
