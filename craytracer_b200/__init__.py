@@ -16,7 +16,7 @@ from ._abi import (BUILD_EXACT, BUILD_FAST, CRAY_NO_HIT, HIT_DTYPE, RAY_DTYPE, S
                    SceneInfo)
 
 __all__ = ["ParserError", "CrayError", "HostScene", "Scene", "parse_scene", "load_scene", "make_rays", "tokenize", "parse_raw_value",
-           "register_standin_mesh", "write_exr", "TRAVERSE_EXACT", "TRAVERSE_FAST", "BUILD_EXACT", "BUILD_FAST", "CRAY_NO_HIT"]
+           "register_standin_mesh", "write_exr", "render_multi", "TRAVERSE_EXACT", "TRAVERSE_FAST", "BUILD_EXACT", "BUILD_FAST", "CRAY_NO_HIT"]
 
 
 class CrayError(RuntimeError):
@@ -138,6 +138,19 @@ def tokenize(text):
 def parse_raw_value(text):
     """RawValue::from_tokens(tokenize(input)) of src/scene_parser.rs:336."""
     return _json_call(_abi.lib().cray_debug_parse_raw_value, text)
+
+
+def render_multi(scenes_, seed=0, sample_begin=0, sample_end=None, mode=TRAVERSE_FAST):
+    """render() on several GPUs of this process: one Scene per device (same description), sample slices per GPU, one NCCL
+    reduce of the films (cray_render_multi).  Returns the film SUM (H, W, 3) f32 and the aggregated statistics."""
+    first = scenes_[0]
+    if sample_end is None:
+        sample_end = first.num_samples
+    film = np.empty((first.height, first.width, 3), dtype=np.float32)
+    handles = (C.c_void_p * len(scenes_))(*[sc._h for sc in scenes_])
+    stats = RenderStats()
+    _check(_abi.lib().cray_render_multi(handles, len(scenes_), mode, seed, sample_begin, sample_end, film.ctypes.data, C.byref(stats)))
+    return film, stats
 
 
 def write_exr(path, film):

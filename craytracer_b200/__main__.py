@@ -6,18 +6,16 @@ Same flags as the reference's `Cli` (--scene/-s, --output, --seed, --preview); -
 SURVEY section 2 marks the minifb preview out of scope).  Meshes named by a scene are resolved against the scene file's
 directory's parent, the current directory and this repository's assets/; meshes that exist nowhere (the reference does not
 ship xyzrgb_dragon.obj / staircase.obj) fall back to the documented procedural stand-ins with a warning.
-With --gpus N > 1 the sample range is split over N processes-free GPU contexts of this process (one scene per device) and the
-films are summed on the host; the multi-process NCCL path is bench.py's."""
+With --gpus N > 1 the scene is replicated on N GPUs of this process, each renders a slice of the sample range, and the films
+are combined by one NCCL reduce (cray_render_multi); bench.py does the same with one process per GPU."""
 import argparse
 import os
 import sys
-import threading
 import time
 
 import numpy as np
 
-from . import Scene, TRAVERSE_EXACT, TRAVERSE_FAST, load_scene, scenes, write_exr
-from .distributed import shard_samples
+from . import Scene, TRAVERSE_EXACT, TRAVERSE_FAST, load_scene, render_multi, scenes, write_exr
 
 
 def find_base_dir(scene_path):
@@ -54,19 +52,10 @@ def main(argv=None):
     sc0 = gpu_scenes[0]
     spp = args.spp if args.spp is not None else sc0.num_samples
     mode = TRAVERSE_EXACT if args.mode == "exact" else TRAVERSE_FAST
-    films, stats = [None] * len(devices), [None] * len(devices)
-
-    def work(k):
-        lo, hi = shard_samples(spp, k, len(devices))
-        films[k], stats[k] = gpu_scenes[k].render(seed=args.seed, sample_begin=lo, sample_end=hi, mode=mode)
-
     t0 = time.time()
-    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(devices))]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    film = np.sum(films, axis=0, dtype=np.float32) / np.float32(max(spp, 1))  # pixels /= num_samples (craytracer.rs:253-259)
+    film, st = render_multi(gpu_scenes, seed=args.seed, sample_begin=0, sample_end=spp, mode=mode)
+    film = film / np.float32(max(spp, 1))  # pixels /= num_samples (craytracer.rs:253-259)
+    stats = [st]
     dt = time.time() - t0
     rays = sum(s.closest_rays + s.shadow_rays for s in stats)
     dropped = sum(s.nan_samples for s in stats)

@@ -986,15 +986,25 @@ int cray_render_device(cray_scene* sc, int mode, uint64_t seed, uint32_t sample_
     return CRAY_OK;
 }
 
+// The scene's own device film (W*H*3 f32), allocated on first use; null on failure (see cray_last_error).
+float* cray_scene_film_f32(cray_scene* sc) {
+    if (!sc || cudaSetDevice(sc->device) != cudaSuccess) { set_error("bad scene / device"); return nullptr; }
+    if (ensure_pool(sc, 1) != CRAY_OK) return nullptr;
+    auto* ps = static_cast<PoolStorage*>(sc->pool);
+    if (!ps->d_film_f32) {  // film size is fixed per scene
+        const cudaError_t e = cudaMalloc(&ps->d_film_f32, (size_t)sc->info.width * sc->info.height * 3 * sizeof(float));
+        if (e != cudaSuccess) { cuda_fail(e, "cudaMalloc(film)"); return nullptr; }
+    }
+    return ps->d_film_f32;
+}
+
 int cray_render(cray_scene* sc, int mode, uint64_t seed, uint32_t sample_begin, uint32_t sample_end, float* rgb_sum, cray_render_stats* stats) {
     if (!sc || !rgb_sum) { set_error("bad arguments"); return CRAY_E_INVALID; }
     CRAY_CUDA(cudaSetDevice(sc->device));
     const uint64_t n = (uint64_t)sc->info.width * sc->info.height * 3;
-    int rc = ensure_pool(sc, 1);
-    if (rc != CRAY_OK) return rc;
+    if (!cray_scene_film_f32(sc)) return CRAY_E_CUDA;
     auto* ps = static_cast<PoolStorage*>(sc->pool);
-    if (!ps->d_film_f32) CRAY_CUDA(cudaMalloc(&ps->d_film_f32, n * sizeof(float)));  // film size is fixed per scene
-    rc = cray_render_device(sc, mode, seed, sample_begin, sample_end, ps->d_film_f32, sc->stream, stats);
+    int rc = cray_render_device(sc, mode, seed, sample_begin, sample_end, ps->d_film_f32, sc->stream, stats);
     if (rc != CRAY_OK) return rc;
     CRAY_CUDA(cudaMemcpyAsync(rgb_sum, ps->d_film_f32, n * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
     CRAY_CUDA(cudaStreamSynchronize(sc->stream));

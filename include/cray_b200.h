@@ -211,6 +211,13 @@ int cray_render(cray_scene*, int mode, uint64_t seed, uint32_t sample_begin, uin
 int cray_render_device(cray_scene*, int mode, uint64_t seed, uint32_t sample_begin, uint32_t sample_end,
                        float* d_rgb_sum, void* stream, cray_render_stats* stats);
 
+/* One frame on n GPUs of this process.  scenes[k] was created on its own device from the same description; GPU k
+ * renders the k-th contiguous slice of [sample_begin, sample_end) for every pixel, the f32 sum films are combined by ONE
+ * ncclReduce(sum) onto scenes[0]'s device and copied to `rgb_sum` (host, W*H*3).  NCCL is loaded at run time (libnccl.so.2);
+ * CRAY_E_UNSUPPORTED if it is not installed.  Counters in `stats` are sums over GPUs, times are the slowest GPU's. */
+int cray_render_multi(cray_scene* const* scenes, int n, int mode, uint64_t seed, uint32_t sample_begin, uint32_t sample_end,
+                      float* rgb_sum, cray_render_stats* stats);
+
 /* ---- output (the EXR save of src/bin/craytracer.rs:367-369) ----------------------- */
 
 /* Writes `rgb` (W*H*3 f32, row-major, linear RGB -- what render() hands to on_render_finish) as an OpenEXR file with three

@@ -293,3 +293,30 @@ def test_full_size_dragon_batches():
     err = np.abs(got - ref) / (np.abs(ref) + 1e-3)
     assert ok.all() and (err.max(axis=1) <= 1e-9).mean() >= 0.999
     gpu.close()
+
+
+def test_render_multi_single_gpu_is_render():
+    """cray_render_multi with one scene is cray_render."""
+    hs, gpu, orc = get_scene("materials")
+    a, sa = c.render_multi([gpu], seed=2, sample_begin=0, sample_end=3)
+    b, sb = gpu.render(seed=2, sample_begin=0, sample_end=3)
+    assert np.array_equal(a, b) and (sa.closest_rays, sa.shadow_rays) == (sb.closest_rays, sb.shadow_rays)
+
+
+def test_render_multi_shards_samples_over_gpus():
+    """SURVEY 8(e) in one process: the scene replicated on every visible GPU, sample slices per GPU, ONE ncclReduce of the f32
+    films.  Needs >= 2 GPUs (the round-end run has one; run with `gpurun --gpus 2`)."""
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    hs = c.parse_scene(scenes.materials(width=160, height=104))
+    replicas = [c.Scene(hs, device=k) for k in range(n)]
+    whole, st = replicas[0].render(seed=4, sample_begin=1, sample_end=11)
+    multi, sm = c.render_multi(replicas, seed=4, sample_begin=1, sample_end=11)
+    assert (sm.samples, sm.closest_rays, sm.shadow_rays, sm.nan_samples) == (st.samples, st.closest_rays, st.shadow_rays, st.nan_samples)
+    assert np.abs(multi - whole).max() <= 1e-5 * max(1.0, float(whole.max()))  # f32 partial sums in a different order
+    again, _ = c.render_multi(replicas, seed=4, sample_begin=1, sample_end=11)   # the communicators are reused
+    assert np.array_equal(again, multi)
+    with pytest.raises(c.CrayError):
+        c.render_multi([replicas[0], replicas[0]], seed=0, sample_begin=0, sample_end=2)  # two scenes on one device
