@@ -74,6 +74,18 @@ int cray_host_scene_load(const char* cry_path, const char* base_dir, cray_host_s
     return cray_host_scene_parse(ss.str().c_str(), base_dir, out);
 }
 
+// sizeof of the ABI structs of include/cray_b200.h, in declaration order: lets a binding (the ctypes mirror, a Rust `repr(C)`
+// block) verify its layout at start-up.  Returns the number of entries written (at most `capacity`).
+int cray_abi_struct_sizes(uint32_t* out, int capacity) {
+    const uint32_t sizes[] = {sizeof(cray_sphere_desc), sizeof(cray_triangle_desc), sizeof(cray_disk_desc), sizeof(cray_primitive_desc),
+                              sizeof(cray_texture_desc), sizeof(cray_image_desc), sizeof(cray_material_desc), sizeof(cray_light_desc),
+                              sizeof(cray_camera_desc), sizeof(cray_scene_desc), sizeof(cray_ray), sizeof(cray_hit), sizeof(cray_surface),
+                              sizeof(cray_render_stats), sizeof(cray_scene_info), sizeof(cray_bvh_node_dump)};
+    const int n = (int)(sizeof(sizes) / sizeof(sizes[0]));
+    for (int i = 0; i < n && i < capacity; ++i) out[i] = sizes[i];
+    return n < capacity ? n : capacity;
+}
+
 // OpenEXR 2.0 single-part scan-line file, channels B, G, R as 32-bit float, NO_COMPRESSION, increasing-y line order.
 int cray_write_exr(const char* path, uint32_t width, uint32_t height, const float* rgb) {
     if (!path || !rgb || width == 0 || height == 0) { cray::set_error("bad arguments"); return CRAY_E_INVALID; }

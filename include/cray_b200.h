@@ -245,6 +245,10 @@ int cray_build_reference_bvh(const cray_scene_desc* desc, cray_bvh_node_dump** n
                              uint32_t** prim_order, uint64_t* n_prims);
 void cray_free(void*);
 
+/* sizeof of the structs above in declaration order (sphere, triangle, disk, primitive, texture, image, material, light, camera,
+ * scene desc, ray, hit, surface, render stats, scene info, bvh node dump): a binding checks its layout against it. */
+int cray_abi_struct_sizes(uint32_t* out, int capacity);
+
 const char* cray_last_error(void);   /* thread-local */
 const char* cray_version(void);
 

@@ -236,3 +236,14 @@ def test_shard_samples_tile_the_range():
             assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in ranges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_ctypes_mirror_matches_the_header_layout():
+    """The structs of craytracer_b200/_abi.py are the same size as the C structs they mirror (cray_abi_struct_sizes)."""
+    out = np.zeros(32, dtype=np.uint32)
+    n = _abi.lib().cray_abi_struct_sizes(out.ctypes.data, 32)
+    mirror = [C.sizeof(_abi.SphereDesc), C.sizeof(_abi.TriangleDesc), C.sizeof(_abi.DiskDesc), C.sizeof(_abi.PrimitiveDesc), C.sizeof(_abi.TextureDesc),
+              C.sizeof(_abi.ImageDesc), C.sizeof(_abi.MaterialDesc), C.sizeof(_abi.LightDesc), C.sizeof(_abi.CameraDesc), C.sizeof(_abi.SceneDesc),
+              _abi.RAY_DTYPE.itemsize, _abi.HIT_DTYPE.itemsize, _abi.SURFACE_DTYPE.itemsize, C.sizeof(_abi.RenderStats), C.sizeof(_abi.SceneInfo),
+              C.sizeof(_abi.BvhNodeDump)]
+    assert n == len(mirror) and list(out[:n]) == mirror
