@@ -439,6 +439,9 @@ __global__ void __launch_bounds__(128) k_extend_exact(SceneView s, Pool p, const
 #ifndef CRAY_SHADE_BLOCKS
 #define CRAY_SHADE_BLOCKS 3
 #endif
+#ifndef CRAY_SHADE_PREFETCH
+#define CRAY_SHADE_PREFETCH 1
+#endif
 constexpr uint32_t kShadeThreads = CRAY_SHADE_THREADS;
 constexpr uint32_t kShadeKeys = 16;   // class (matte, glass, plastic, metal) x shape kind (3); 12 = miss; 13 = no path
 
@@ -459,8 +462,17 @@ __global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(Scen
             const uint32_t my_slot = p.hit_slot[mine];
             key = 12u;
             if (my_slot != CRAY_NO_HIT) {
-                const uint32_t kind = __ldg(&(job.exact ? s.bin_prims : s.wide_prims)[my_slot].kind);
+                const LeafPrim* rec = (job.exact ? s.bin_prims : s.wide_prims) + my_slot;
+                const uint2 prim_kind = __ldg(reinterpret_cast<const uint2*>(&rec->prim));
+                const uint32_t kind = prim_kind.y;
                 key = ((kind >> 8) & 3u) * 3u + (kind & 3u);
+#if CRAY_SHADE_PREFETCH
+                // whichever thread of this block shades the path will read the intersection record and, for a triangle, the first
+                // sector of its shading record: start those loads now, a sort and two barriers ahead of their use
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(rec));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(rec) + 64));
+                if ((kind & 0xFFu) == PRIM_TRIANGLE) asm volatile("prefetch.global.L1 [%0];" ::"l"(s.tri_shade + prim_kind.x));
+#endif
             }
         }
         if (threadIdx.x < kCells) s_count[threadIdx.x] = 0u;

@@ -30,7 +30,12 @@ def main():
     shadow, cont = orc.bounce_rays(xs, ys, ss)
     print(f"oracle produced {len(cont)} continuation and {len(shadow)} shadow rays in {time.time() - t0:.1f} s")
     rng = np.random.default_rng(0)
-    for name, rays, closest in (("continuation", cont, True), ("shadow", shadow, False)):
+    primary = orc.camera_rays(xs, ys, ss)
+    mixed = np.concatenate([primary, cont])
+    interleaved = np.empty_like(mixed)  # what the wavefront queue looks like: fresh camera rays scattered among continuing paths
+    perm = rng.permutation(len(mixed))
+    interleaved[:] = mixed[perm]
+    for name, rays, closest in (("primary", primary, True), ("primary+cont", mixed, True), ("continuation", cont, True), ("shadow", shadow, False)):
         for label, arr in (("tile order", rays), ("shuffled", rays[rng.permutation(len(rays))])):
             d_rays = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).cuda()
             d_out = torch.empty(len(arr) * 32, dtype=torch.uint8, device="cuda")
