@@ -320,3 +320,26 @@ def test_render_multi_shards_samples_over_gpus():
     assert np.array_equal(again, multi)
     with pytest.raises(c.CrayError):
         c.render_multi([replicas[0], replicas[0]], seed=0, sample_begin=0, sample_end=2)  # two scenes on one device
+
+
+def test_api_argument_errors():
+    """Bad arguments come back as error codes with a message, never as a crash (the reference panics)."""
+    hs, gpu, orc = get_scene("test")
+    rays = random_rays([-1, -1, -3], [4, 3, 1], 16, seed=0)
+    with pytest.raises(c.CrayError) as e:
+        gpu.intersect(rays, mode=7)
+    assert e.value.code == c._abi.CRAY_E_INVALID
+    with pytest.raises(c.CrayError) as e:
+        gpu.render(seed=0, sample_begin=0, sample_end=65537)          # sobol_burley has 2^16 points (sampling.rs:197-247)
+    assert "2^16" in e.value.message
+    with pytest.raises(c.CrayError):
+        gpu.render(seed=0, sample_begin=5, sample_end=2)
+    exact_only = c.Scene(hs, build=c.BUILD_EXACT)
+    with pytest.raises(c.CrayError) as e:
+        exact_only.intersect(rays, mode=c.TRAVERSE_FAST)
+    assert "CRAY_BUILD_FAST" in e.value.message
+    assert len(exact_only.intersect(rays, mode=c.TRAVERSE_EXACT)) == 16
+    film, st = gpu.render(seed=0, sample_begin=65535, sample_end=65536)  # the last sample index is valid
+    assert st.samples == gpu.width * gpu.height and np.isfinite(film).all()
+    with pytest.raises(c.CrayError):
+        c.Scene(hs, device=99)
