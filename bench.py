@@ -37,7 +37,7 @@ def measured_peaks():
 
 
 def profiled_traffic():
-    """dram bytes per k_extend launch from the committed ncu summary of this workload, if any."""
+    """dram bytes per launch of the extend kernel (k_wide_persistent<false>) from the committed ncu summary of this workload, if any."""
     try:
         with open(os.path.join(ROOT, "profiles", "extend_traffic.json")) as f:
             return json.load(f)
@@ -297,7 +297,7 @@ def run_ours(args):
         samples = args.width * args.height * args.spp * args.steps
         value = rays / ms_dev / 1e3
         peak, peak_kind = measured_peaks()
-        # dominant kernel: k_extend (closest-hit traversal); CUDA-event time of its launches on rank 0 inside the timed region
+        # dominant kernel: k_wide_persistent<false> (closest-hit traversal); CUDA-event time of its launches on rank 0 inside the timed region
         extend_ms = totals["trace_ms"]
         achieved = totals["closest"] * ALGORITHMIC_BYTES_PER_RAY / (extend_ms * 1e-3) / 1e9 if extend_ms > 0 else 0.0
         traffic = profiled_traffic()

@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(Scen
         }
     }
     // assert!(L.is_finite()); assert!(beta.is_finite()) (:208-209).  L still lacks this vertex's light sample, which
-    // k_shadow adds; k_generate re-checks L when the path is flushed.
+    // the shadow stage adds; k_generate re-checks L when the path is flushed.
     if (!is_finite3(L) || !is_finite3(beta)) { bad = true; finish(L, shadow_pending); return; }
 
     const uint32_t next_bounces = bounces + 1;
