@@ -175,11 +175,14 @@ def make_rays(origins, directions, max_distance=np.inf):
 class Scene:
     """GPU-resident scene: Scene::new (src/scene.rs:25) + the S1/S2/S3 entry points."""
 
-    def __init__(self, host_scene, device=0, build=BUILD_EXACT | BUILD_FAST):
+    def __init__(self, host_scene, device=0, build=BUILD_EXACT | BUILD_FAST, _handle=None):
         desc_ptr = host_scene.desc_ptr if isinstance(host_scene, HostScene) else host_scene
         self._keep = host_scene
-        h = C.c_void_p()
-        _check(_abi.lib().cray_scene_create(desc_ptr, int(device), int(build), C.byref(h)))
+        if _handle is None:
+            h = C.c_void_p()
+            _check(_abi.lib().cray_scene_create(desc_ptr, int(device), int(build), C.byref(h)))
+        else:
+            h = _handle
         self._h = h
         info = SceneInfo()
         _check(_abi.lib().cray_scene_get_info(self._h, C.byref(info)))
@@ -187,6 +190,15 @@ class Scene:
         self.width, self.height = info.width, info.height
         self.max_depth, self.num_samples = info.max_depth, info.num_samples
         self.device = device
+
+    @classmethod
+    def create_multi(cls, host_scene, devices, build=BUILD_EXACT | BUILD_FAST):
+        """One Scene per device from a single host-side build (cray_scene_create_multi); feed the list to render_multi."""
+        desc_ptr = host_scene.desc_ptr if isinstance(host_scene, HostScene) else host_scene
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        handles = (C.c_void_p * len(devices))()
+        _check(_abi.lib().cray_scene_create_multi(desc_ptr, devs, len(devices), int(build), handles))
+        return [cls(host_scene, device=int(d), build=build, _handle=C.c_void_p(handles[k])) for k, d in enumerate(devices)]
 
     def close(self):
         if getattr(self, "_h", None):

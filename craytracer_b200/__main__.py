@@ -46,7 +46,7 @@ def main(argv=None):
     for w in hs.warnings:
         print(f"[WARN] {w}", file=sys.stderr)
     devices = list(range(max(1, args.gpus)))
-    gpu_scenes = [Scene(hs, device=d) for d in devices]
+    gpu_scenes = Scene.create_multi(hs, devices)
     print(f"[INFO] Scene constructed in {time.time() - start:.3f}s", file=sys.stderr)
 
     sc0 = gpu_scenes[0]

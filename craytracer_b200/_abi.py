@@ -114,6 +114,7 @@ SIGNATURES = {
     "cray_trace_closest_device": (C.c_int, [_P, C.c_int, _P, C.c_uint64, _P, _P, _P]),
     "cray_trace_any_device": (C.c_int, [_P, C.c_int, _P, C.c_uint64, _P, _P]),
     "cray_estimate_li": (C.c_int, [_P, C.c_int, C.c_uint64, _P, _P, _P, C.c_uint64, _P]),
+    "cray_scene_create_multi": (C.c_int, [C.POINTER(SceneDesc), _P, C.c_int, C.c_uint32, _P]),
     "cray_render_multi": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, _P, C.POINTER(RenderStats)]),
     "cray_abi_struct_sizes": (C.c_int, [_P, C.c_int]),
     "cray_write_exr": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, _P]),

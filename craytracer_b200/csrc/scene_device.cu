@@ -167,6 +167,259 @@ int validate(const cray_scene_desc* d) {
     return CRAY_OK;
 }
 
+// Everything cray_scene_create derives from a description on the host: built once, uploaded to one or several devices.
+struct HostBuild {
+    uint32_t build_flags = 0;
+    RefBvh ref;
+    WideBvh wide;
+    std::vector<LeafPrim> bin_prims, wide_prims;
+    std::vector<uint32_t> rank_of_prim;
+    std::vector<DiskXf> disks;
+    std::vector<TriShade> tri_shade;
+    std::vector<DevMaterial> materials;
+    std::vector<cray_primitive_desc> prims;
+    std::vector<DevImage> images;
+    std::vector<uint8_t> texels;
+    std::vector<double> gamma_lut;
+    std::vector<DevLight> lights;
+    std::vector<double> cdf;
+    std::vector<uint32_t> pixel_order, sobol;
+    std::vector<cray_sphere_desc> spheres;
+    DevCamera cam{};
+    double build_ms = 0.0;
+};
+
+// Scene::new (scene.rs:25-53) on the host: the reference BVH, its wide collapse, and every flat array of device_types.cuh.
+int build_host_side(const cray_scene_desc* d, uint32_t build_flags, HostBuild& hb) {
+    hb.build_flags = build_flags;
+    RefBvh& ref = hb.ref;
+    WideBvh& wide = hb.wide;
+    auto t0 = std::chrono::steady_clock::now();
+    build_reference_bvh(*d, ref);
+    if (!ref.error.empty()) { set_error(ref.error); return CRAY_E_BVH; }
+    if (build_flags & CRAY_BUILD_FAST) {
+        collapse_to_wide(*d, ref, wide);
+        if (wide.depth >= (uint32_t)kWideStackLimit) { set_error("wide BVH deeper than the traversal stack"); return CRAY_E_BVH; }
+        if (d->n_primitives >= (1ull << 27)) { set_error("more than 2^27 primitives: the fast traversal's queue entries hold 27-bit leaf slots"); return CRAY_E_UNSUPPORTED; }
+    }
+    hb.build_ms = ms_since(t0);
+    PhaseTimer timer;
+    const size_t np = (size_t)d->n_primitives;
+    // leaf-ordered intersection records
+    std::vector<LeafPrim>& bin_prims = hb.bin_prims;
+    std::vector<LeafPrim>& wide_prims = hb.wide_prims;
+    std::vector<uint32_t>& rank_of_prim = hb.rank_of_prim;
+    bin_prims.resize(np); wide_prims.resize(wide.prim_order.size()); rank_of_prim.resize(np);
+    {
+        const unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+        std::vector<std::thread> pool;
+        auto work = [&](unsigned t) {
+            for (size_t i = t; i < np; i += nt) {
+                bin_prims[i] = make_leaf_prim(*d, ref.prim_order[i]);
+                rank_of_prim[ref.prim_order[i]] = (uint32_t)i;
+                if (!wide_prims.empty()) wide_prims[i] = make_leaf_prim(*d, wide.prim_order[i]);
+            }
+        };
+        for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (auto& th : pool) th.join();
+    }
+    timer.mark("leaf records");
+    std::vector<DiskXf>& disks = hb.disks;
+    disks.resize(d->n_disks);
+    for (size_t i = 0; i < disks.size(); ++i) disks[i] = make_disk(d->disks[i]);
+    // per-primitive shading records for triangles (flat ones are flagged in their LeafPrim, see make_leaf_prim)
+    std::vector<TriShade>& tri_shade = hb.tri_shade;
+    tri_shade.resize(d->n_triangles ? np : 0);
+    {
+        const unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+        std::vector<std::thread> pool;
+        auto work = [&](unsigned t0) {
+            for (size_t i = t0; i < tri_shade.size(); i += nt) {
+                const cray_primitive_desc& p = d->primitives[i];
+                TriShade& ts = tri_shade[i];
+                std::memset(&ts, 0, sizeof(ts));
+                if (p.shape_kind != CRAY_SHAPE_TRIANGLE) continue;
+                const cray_triangle_desc& t = d->triangles[p.shape_index];
+                std::memcpy(ts.n0, t.n0, 24); std::memcpy(ts.n01, t.n01, 24); std::memcpy(ts.n02, t.n02, 24);
+                std::memcpy(ts.uv0, t.uv0, 16); std::memcpy(ts.uv01, t.uv01, 16); std::memcpy(ts.uv02, t.uv02, 16);
+                ts.material = p.area_light >= 0 ? (int32_t)d->n_materials : p.material;
+                ts.area_light = p.area_light;
+            }
+        };
+        for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (auto& th : pool) th.join();
+    }
+    timer.mark("shading records");
+    // materials (+ the black matte that area-light primitives carry, primitive.rs:43-46)
+    std::vector<DevMaterial>& materials = hb.materials;
+    materials.resize(d->n_materials + 1);
+    for (size_t i = 0; i < d->n_materials; ++i) materials[i] = make_material(d->materials[i]);
+    {
+        cray_material_desc black{};
+        black.kind = CRAY_MAT_MATTE;
+        black.t0.kind = black.t1.kind = black.t2.kind = CRAY_TEX_CONSTANT;
+        materials[d->n_materials] = make_material(black);
+    }
+    std::vector<cray_primitive_desc>& prims = hb.prims;
+    prims.assign(d->primitives, d->primitives + np);
+    for (auto& p : prims)
+        if (p.area_light >= 0) p.material = (int32_t)d->n_materials;
+    // images
+    std::vector<DevImage>& images = hb.images;
+    images.resize(d->n_images);
+    std::vector<uint8_t>& texels = hb.texels;
+    for (size_t i = 0; i < images.size(); ++i) {
+        images[i] = {d->images[i].width, d->images[i].height, (uint64_t)texels.size()};
+        const size_t bytes = (size_t)d->images[i].width * d->images[i].height * 3;
+        texels.insert(texels.end(), d->images[i].rgb, d->images[i].rgb + bytes);
+    }
+    std::vector<double>& gamma_lut = hb.gamma_lut;
+    gamma_lut.resize(256);
+    for (int c = 0; c < 256; ++c) gamma_lut[c] = std::pow((double)c / 255.0, 2.2);  // Color::from_rgb color.rs:39-46
+    // lights + LightSampler::new (light.rs:187-199); world radius = half the BVH diagonal (scene.rs:42)
+    const double world_radius = magnitude(ref.bounds.hi - ref.bounds.lo) * 0.5;
+    std::vector<DevLight>& lights = hb.lights;
+    std::vector<double>& cdf = hb.cdf;
+    lights.resize(d->n_lights); cdf.resize(d->n_lights);
+    double total_power = 0.0;
+    for (size_t i = 0; i < lights.size(); ++i) {
+        const cray_light_desc& l = d->lights[i];
+        DevLight dl{};
+        dl.kind = l.kind;
+        dl.prim = l.primitive;
+        std::memcpy(dl.v, l.v, 24);
+        std::memcpy(dl.color, l.color, 24);
+        Color3 c = mkc(l.color[0], l.color[1], l.color[2]), power;
+        switch (l.kind) {  // Light::power light.rs:170-177
+            case CRAY_LIGHT_POINT: power = c * 4.0 * kPi; break;
+            case CRAY_LIGHT_DISTANT:
+            case CRAY_LIGHT_INFINITE: power = c * kPi * world_radius * world_radius; break;
+            default:
+                dl.shape = make_leaf_prim(*d, (uint32_t)l.primitive);
+                dl.area = shape_area(*d, d->primitives[l.primitive]);
+                power = c * kPi * dl.area;
+                break;
+        }
+        const double power_avg = (power.r + power.g + power.b) / 3.0;
+        total_power += power_avg;
+        cdf[i] = total_power;
+        lights[i] = dl;
+    }
+    for (double& c : cdf) c = c / total_power;
+    // camera (camera.rs:55-129)
+    DevCamera& cam = hb.cam;
+    {
+        const cray_camera_desc& c = d->camera;
+        const Xform wfc = xf_look_at(v3(c.origin), v3(c.target), v3(c.up));
+        const Xform sfc = c.kind == CRAY_CAMERA_PERSPECTIVE ? xf_perspective(c.fov, 1e-2, 1000.0) : xf_orthographic(0.0, 1.0);
+        const Xform cfr = camera_from_raster(sfc, c.width);
+        std::memcpy(cam.camera_from_raster, cfr.fwd.m, sizeof(cam.camera_from_raster));
+        cam.world_from_camera = affine_of(wfc.fwd);
+        cam.lens_radius = c.lens_radius;
+        cam.focal_distance = c.focal_distance;
+        cam.perspective = c.kind == CRAY_CAMERA_PERSPECTIVE;
+        cam.width = c.width;
+        cam.height = c.height;
+    }
+    // pixel order: 8 x 4 pixel tiles (one warp = one tile), tiles row-major
+    std::vector<uint32_t>& pixel_order = hb.pixel_order;
+    pixel_order.reserve((size_t)cam.width * cam.height);
+    for (uint32_t ty = 0; ty < cam.height; ty += 4)
+        for (uint32_t tx = 0; tx < cam.width; tx += 8)
+            for (uint32_t y = ty; y < std::min(ty + 4, cam.height); ++y)
+                for (uint32_t x = tx; x < std::min(tx + 8, cam.width); ++x) pixel_order.push_back(x | (y << 16));
+    // Sobol direction vectors folded into byte tables (sampler.cuh:sobol_sample): [dimension][half][byte]
+#if !CRAY_SOBOL_BYTES
+    std::vector<uint32_t>& sobol = hb.sobol;
+    sobol.assign(&SOBOL_DIRECTIONS_INIT[0][0], &SOBOL_DIRECTIONS_INIT[0][0] + 256 * 32);
+#else
+    std::vector<uint32_t>& sobol = hb.sobol;
+    sobol.resize(256 * 512);
+    for (uint32_t dim = 0; dim < 256; ++dim)
+        for (uint32_t half = 0; half < 2; ++half)
+            for (uint32_t b = 0; b < 256; ++b) {
+                uint32_t acc = 0;
+                for (uint32_t j = 0; j < 8; ++j)
+                    if (b & (0x80u >> j)) acc ^= SOBOL_DIRECTIONS_INIT[dim][8 * half + j];
+                sobol[dim * 512 + half * 256 + b] = acc;
+            }
+#endif
+
+    timer.mark("materials, lights, camera");
+    hb.spheres.assign(d->spheres, d->spheres + d->n_spheres);
+    return CRAY_OK;
+}
+
+// One device copy of a HostBuild.
+int upload_scene(const HostBuild& hb, const cray_scene_desc* d, int device, cray_scene** out) {
+    CRAY_CUDA(cudaSetDevice(device));
+    const auto t0 = std::chrono::steady_clock::now();
+    PhaseTimer timer;
+    auto sc = new cray_scene();
+    sc->device = device;
+    sc->build_flags = hb.build_flags;
+    struct Guard { cray_scene* s; ~Guard() { if (s) cray_scene_destroy(s); } } guard{sc};
+    CRAY_CUDA(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
+    SceneView& v = sc->view;
+    const uint32_t* d_order = nullptr;
+    const uint32_t* d_sobol = nullptr;
+    int rc = CRAY_OK;
+#define UP(vec, field) do { rc = upload(sc, vec, &field); if (rc != CRAY_OK) return rc; } while (0)
+    UP(hb.ref.nodes, v.bin_nodes);
+    UP(hb.bin_prims, v.bin_prims);
+    UP(hb.wide.nodes, v.wide_nodes);
+    UP(hb.wide_prims, v.wide_prims);
+    UP(hb.rank_of_prim, v.rank_of_prim);
+    UP(hb.disks, v.disks);
+    UP(hb.prims, v.prims);
+    UP(hb.tri_shade, v.tri_shade);
+    UP(hb.spheres, v.spheres);
+    UP(hb.materials, v.materials);
+    UP(hb.images, v.images);
+    UP(hb.texels, v.texels);
+    UP(hb.gamma_lut, v.gamma_lut);
+    UP(hb.lights, v.lights);
+    UP(hb.cdf, v.light_cdf);
+    UP(hb.pixel_order, d_order);
+    UP(hb.sobol, d_sobol);
+#undef UP
+    sc->d_pixel_order = const_cast<uint32_t*>(d_order);
+    sc->d_sobol = const_cast<uint32_t*>(d_sobol);
+    v.n_lights = (uint32_t)d->n_lights;
+    v.max_depth = d->max_depth;
+    v.camera = hb.cam;
+    v.bounds = hb.ref.bounds;
+    CRAY_CUDA(cudaDeviceSynchronize());
+    timer.mark("upload");
+
+    cray_scene_info& info = sc->info;
+    info.n_primitives = d->n_primitives;
+    info.n_lights = d->n_lights;
+    info.exact_nodes = hb.ref.nodes.size();
+    info.exact_bytes = hb.ref.nodes.size() * sizeof(BinNode);
+    info.wide_nodes = hb.wide.nodes.size();
+    info.wide_bytes = hb.wide.nodes.size() * sizeof(WideNode);
+    info.leaf_prim_bytes = (uint64_t)d->n_primitives * sizeof(LeafPrim);
+    info.wide_depth = hb.wide.depth;
+    info.width = hb.cam.width; info.height = hb.cam.height;
+    info.max_depth = d->max_depth; info.num_samples = d->num_samples;
+    info.bvh_build_ms = hb.build_ms;
+    info.upload_ms = ms_since(t0);
+    guard.s = nullptr;
+    *out = sc;
+    return CRAY_OK;
+}
+
+int check_devices(const int* devices, int n) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { set_error("no CUDA device available (this library has no CPU fallback)"); return CRAY_E_CUDA; }
+    for (int k = 0; k < n; ++k)
+        if (devices[k] < 0 || devices[k] >= count) { set_error("CUDA device index out of range"); return CRAY_E_INVALID; }
+    return CRAY_OK;
+}
+
 }  // namespace
 }  // namespace cray
 
@@ -206,217 +459,39 @@ void cray_scene_destroy(cray_scene* sc) {
 }
 
 int cray_scene_create(const cray_scene_desc* d, int device, uint32_t build_flags, cray_scene** out) {
-    if (!out) { set_error("null output handle"); return CRAY_E_INVALID; }
-    *out = nullptr;
+    return cray_scene_create_multi(d, &device, 1, build_flags, out);
+}
+
+// The same scene on several devices of this process: the host side (BVH build, record arrays) runs once.
+int cray_scene_create_multi(const cray_scene_desc* d, const int* devices, int n, uint32_t build_flags, cray_scene** out) {
+    if (!out || !devices || n <= 0) { set_error("bad arguments"); return CRAY_E_INVALID; }
+    for (int k = 0; k < n; ++k) out[k] = nullptr;
     int rc = validate(d);
     if (rc != CRAY_OK) return rc;
     if (build_flags == 0) build_flags = CRAY_BUILD_EXACT | CRAY_BUILD_FAST;
     build_flags |= CRAY_BUILD_EXACT;  // the binary tree also resolves exact-t ties for the fast mode
-    int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { set_error("no CUDA device available (this library has no CPU fallback)"); return CRAY_E_CUDA; }
-    if (device < 0 || device >= count) { set_error("CUDA device index out of range"); return CRAY_E_INVALID; }
-    CRAY_CUDA(cudaSetDevice(device));
-
-    auto t0 = std::chrono::steady_clock::now();
-    RefBvh ref;
-    build_reference_bvh(*d, ref);
-    if (!ref.error.empty()) { set_error(ref.error); return CRAY_E_BVH; }
-    WideBvh wide;
-    if (build_flags & CRAY_BUILD_FAST) {
-        collapse_to_wide(*d, ref, wide);
-        if (wide.depth >= (uint32_t)kWideStackLimit) { set_error("wide BVH deeper than the traversal stack"); return CRAY_E_BVH; }
-        if (d->n_primitives >= (1ull << 27)) { set_error("more than 2^27 primitives: the fast traversal's queue entries hold 27-bit leaf slots"); return CRAY_E_UNSUPPORTED; }
-    }
-    const double build_ms = ms_since(t0);
-    t0 = std::chrono::steady_clock::now();
-
-    auto sc = new cray_scene();
-    sc->device = device;
-    sc->build_flags = build_flags;
-    struct Guard { cray_scene* s; ~Guard() { if (s) cray_scene_destroy(s); } } guard{sc};
-    CRAY_CUDA(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
-
-    PhaseTimer timer;
-    const size_t np = (size_t)d->n_primitives;
-    // leaf-ordered intersection records
-    std::vector<LeafPrim> bin_prims(np), wide_prims(wide.prim_order.size());
-    std::vector<uint32_t> rank_of_prim(np);
-    {
-        const unsigned nt = std::max(1u, std::thread::hardware_concurrency());
-        std::vector<std::thread> pool;
-        auto work = [&](unsigned t) {
-            for (size_t i = t; i < np; i += nt) {
-                bin_prims[i] = make_leaf_prim(*d, ref.prim_order[i]);
-                rank_of_prim[ref.prim_order[i]] = (uint32_t)i;
-                if (!wide_prims.empty()) wide_prims[i] = make_leaf_prim(*d, wide.prim_order[i]);
-            }
-        };
-        for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t);
-        work(0);
-        for (auto& th : pool) th.join();
-    }
-    timer.mark("leaf records");
-    std::vector<DiskXf> disks(d->n_disks);
-    for (size_t i = 0; i < disks.size(); ++i) disks[i] = make_disk(d->disks[i]);
-    // per-primitive shading records for triangles (flat ones are flagged in their LeafPrim, see make_leaf_prim)
-    std::vector<TriShade> tri_shade(d->n_triangles ? np : 0);
-    {
-        const unsigned nt = std::max(1u, std::thread::hardware_concurrency());
-        std::vector<std::thread> pool;
-        auto work = [&](unsigned t0) {
-            for (size_t i = t0; i < tri_shade.size(); i += nt) {
-                const cray_primitive_desc& p = d->primitives[i];
-                TriShade& ts = tri_shade[i];
-                std::memset(&ts, 0, sizeof(ts));
-                if (p.shape_kind != CRAY_SHAPE_TRIANGLE) continue;
-                const cray_triangle_desc& t = d->triangles[p.shape_index];
-                std::memcpy(ts.n0, t.n0, 24); std::memcpy(ts.n01, t.n01, 24); std::memcpy(ts.n02, t.n02, 24);
-                std::memcpy(ts.uv0, t.uv0, 16); std::memcpy(ts.uv01, t.uv01, 16); std::memcpy(ts.uv02, t.uv02, 16);
-                ts.material = p.area_light >= 0 ? (int32_t)d->n_materials : p.material;
-                ts.area_light = p.area_light;
-            }
-        };
-        for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t);
-        work(0);
-        for (auto& th : pool) th.join();
-    }
-    timer.mark("shading records");
-    // materials (+ the black matte that area-light primitives carry, primitive.rs:43-46)
-    std::vector<DevMaterial> materials(d->n_materials + 1);
-    for (size_t i = 0; i < d->n_materials; ++i) materials[i] = make_material(d->materials[i]);
-    {
-        cray_material_desc black{};
-        black.kind = CRAY_MAT_MATTE;
-        black.t0.kind = black.t1.kind = black.t2.kind = CRAY_TEX_CONSTANT;
-        materials[d->n_materials] = make_material(black);
-    }
-    std::vector<cray_primitive_desc> prims(d->primitives, d->primitives + np);
-    for (auto& p : prims)
-        if (p.area_light >= 0) p.material = (int32_t)d->n_materials;
-    // images
-    std::vector<DevImage> images(d->n_images);
-    std::vector<uint8_t> texels;
-    for (size_t i = 0; i < images.size(); ++i) {
-        images[i] = {d->images[i].width, d->images[i].height, (uint64_t)texels.size()};
-        const size_t bytes = (size_t)d->images[i].width * d->images[i].height * 3;
-        texels.insert(texels.end(), d->images[i].rgb, d->images[i].rgb + bytes);
-    }
-    std::vector<double> gamma_lut(256);
-    for (int c = 0; c < 256; ++c) gamma_lut[c] = std::pow((double)c / 255.0, 2.2);  // Color::from_rgb color.rs:39-46
-    // lights + LightSampler::new (light.rs:187-199); world radius = half the BVH diagonal (scene.rs:42)
-    const double world_radius = magnitude(ref.bounds.hi - ref.bounds.lo) * 0.5;
-    std::vector<DevLight> lights(d->n_lights);
-    std::vector<double> cdf(d->n_lights);
-    double total_power = 0.0;
-    for (size_t i = 0; i < lights.size(); ++i) {
-        const cray_light_desc& l = d->lights[i];
-        DevLight dl{};
-        dl.kind = l.kind;
-        dl.prim = l.primitive;
-        std::memcpy(dl.v, l.v, 24);
-        std::memcpy(dl.color, l.color, 24);
-        Color3 c = mkc(l.color[0], l.color[1], l.color[2]), power;
-        switch (l.kind) {  // Light::power light.rs:170-177
-            case CRAY_LIGHT_POINT: power = c * 4.0 * kPi; break;
-            case CRAY_LIGHT_DISTANT:
-            case CRAY_LIGHT_INFINITE: power = c * kPi * world_radius * world_radius; break;
-            default:
-                dl.shape = make_leaf_prim(*d, (uint32_t)l.primitive);
-                dl.area = shape_area(*d, d->primitives[l.primitive]);
-                power = c * kPi * dl.area;
-                break;
+    rc = check_devices(devices, n);
+    if (rc != CRAY_OK) return rc;
+    HostBuild hb;
+    rc = build_host_side(d, build_flags, hb);
+    if (rc != CRAY_OK) return rc;
+    // one uploading thread per device (cray_last_error is thread-local: carry a failure back to this thread)
+    std::vector<int> rcs(n, CRAY_OK);
+    std::vector<std::string> errors(n);
+    std::vector<std::thread> pool;
+    auto work = [&](int k) {
+        rcs[k] = upload_scene(hb, d, devices[k], &out[k]);
+        if (rcs[k] != CRAY_OK) errors[k] = last_error();
+    };
+    for (int k = 1; k < n; ++k) pool.emplace_back(work, k);
+    work(0);
+    for (auto& th : pool) th.join();
+    for (int k = 0; k < n; ++k)
+        if (rcs[k] != CRAY_OK) {
+            for (int j = 0; j < n; ++j) { if (out[j]) cray_scene_destroy(out[j]); out[j] = nullptr; }
+            set_error(errors[k]);
+            return rcs[k];
         }
-        const double power_avg = (power.r + power.g + power.b) / 3.0;
-        total_power += power_avg;
-        cdf[i] = total_power;
-        lights[i] = dl;
-    }
-    for (double& c : cdf) c = c / total_power;
-    // camera (camera.rs:55-129)
-    DevCamera cam{};
-    {
-        const cray_camera_desc& c = d->camera;
-        const Xform wfc = xf_look_at(v3(c.origin), v3(c.target), v3(c.up));
-        const Xform sfc = c.kind == CRAY_CAMERA_PERSPECTIVE ? xf_perspective(c.fov, 1e-2, 1000.0) : xf_orthographic(0.0, 1.0);
-        const Xform cfr = camera_from_raster(sfc, c.width);
-        std::memcpy(cam.camera_from_raster, cfr.fwd.m, sizeof(cam.camera_from_raster));
-        cam.world_from_camera = affine_of(wfc.fwd);
-        cam.lens_radius = c.lens_radius;
-        cam.focal_distance = c.focal_distance;
-        cam.perspective = c.kind == CRAY_CAMERA_PERSPECTIVE;
-        cam.width = c.width;
-        cam.height = c.height;
-    }
-    // pixel order: 8 x 4 pixel tiles (one warp = one tile), tiles row-major
-    std::vector<uint32_t> pixel_order;
-    pixel_order.reserve((size_t)cam.width * cam.height);
-    for (uint32_t ty = 0; ty < cam.height; ty += 4)
-        for (uint32_t tx = 0; tx < cam.width; tx += 8)
-            for (uint32_t y = ty; y < std::min(ty + 4, cam.height); ++y)
-                for (uint32_t x = tx; x < std::min(tx + 8, cam.width); ++x) pixel_order.push_back(x | (y << 16));
-    // Sobol direction vectors folded into byte tables (sampler.cuh:sobol_sample): [dimension][half][byte]
-#if !CRAY_SOBOL_BYTES
-    std::vector<uint32_t> sobol(&SOBOL_DIRECTIONS_INIT[0][0], &SOBOL_DIRECTIONS_INIT[0][0] + 256 * 32);
-#else
-    std::vector<uint32_t> sobol(256 * 512);
-    for (uint32_t dim = 0; dim < 256; ++dim)
-        for (uint32_t half = 0; half < 2; ++half)
-            for (uint32_t b = 0; b < 256; ++b) {
-                uint32_t acc = 0;
-                for (uint32_t j = 0; j < 8; ++j)
-                    if (b & (0x80u >> j)) acc ^= SOBOL_DIRECTIONS_INIT[dim][8 * half + j];
-                sobol[dim * 512 + half * 256 + b] = acc;
-            }
-#endif
-
-    timer.mark("materials, lights, camera");
-    SceneView& v = sc->view;
-    const uint32_t* d_order = nullptr;
-    const uint32_t* d_sobol = nullptr;
-    std::vector<cray_sphere_desc> spheres(d->spheres, d->spheres + d->n_spheres);
-#define UP(vec, field) do { rc = upload(sc, vec, &field); if (rc != CRAY_OK) return rc; } while (0)
-    UP(ref.nodes, v.bin_nodes);
-    UP(bin_prims, v.bin_prims);
-    UP(wide.nodes, v.wide_nodes);
-    UP(wide_prims, v.wide_prims);
-    UP(rank_of_prim, v.rank_of_prim);
-    UP(disks, v.disks);
-    UP(prims, v.prims);
-    UP(tri_shade, v.tri_shade);
-    UP(spheres, v.spheres);
-    UP(materials, v.materials);
-    UP(images, v.images);
-    UP(texels, v.texels);
-    UP(gamma_lut, v.gamma_lut);
-    UP(lights, v.lights);
-    UP(cdf, v.light_cdf);
-    UP(pixel_order, d_order);
-    UP(sobol, d_sobol);
-#undef UP
-    sc->d_pixel_order = const_cast<uint32_t*>(d_order);
-    sc->d_sobol = const_cast<uint32_t*>(d_sobol);
-    v.n_lights = (uint32_t)d->n_lights;
-    v.max_depth = d->max_depth;
-    v.camera = cam;
-    v.bounds = ref.bounds;
-    CRAY_CUDA(cudaDeviceSynchronize());
-    timer.mark("upload");
-
-    cray_scene_info& info = sc->info;
-    info.n_primitives = np;
-    info.n_lights = d->n_lights;
-    info.exact_nodes = ref.nodes.size();
-    info.exact_bytes = ref.nodes.size() * sizeof(BinNode);
-    info.wide_nodes = wide.nodes.size();
-    info.wide_bytes = wide.nodes.size() * sizeof(WideNode);
-    info.leaf_prim_bytes = np * sizeof(LeafPrim);
-    info.wide_depth = wide.depth;
-    info.width = cam.width; info.height = cam.height;
-    info.max_depth = d->max_depth; info.num_samples = d->num_samples;
-    info.bvh_build_ms = build_ms;
-    info.upload_ms = ms_since(t0);
-    guard.s = nullptr;
-    *out = sc;
     return CRAY_OK;
 }
 

@@ -149,6 +149,9 @@ typedef struct cray_scene cray_scene;   /* opaque; owns all device memory on its
 #define CRAY_BUILD_FAST 2u    /* 8-wide quantised BVH collapsed from the same tree */
 
 int cray_scene_create(const cray_scene_desc* desc, int device, uint32_t build_flags, cray_scene** out);
+/* The same scene on n devices of this process (for cray_render_multi): the BVH build and the record arrays are made once
+ * on the host and uploaded to every device by its own thread.  out[0..n) are all set, or all null on failure. */
+int cray_scene_create_multi(const cray_scene_desc* desc, const int* devices, int n, uint32_t build_flags, cray_scene** out);
 void cray_scene_destroy(cray_scene*);
 
 /* ---- S3: fixed ray batches (Scene::intersect / intersects, src/scene.rs:55,:59) */

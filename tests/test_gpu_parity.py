@@ -311,7 +311,7 @@ def test_render_multi_shards_samples_over_gpus():
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     hs = c.parse_scene(scenes.materials(width=160, height=104))
-    replicas = [c.Scene(hs, device=k) for k in range(n)]
+    replicas = c.Scene.create_multi(hs, list(range(n)))  # one host-side build, uploaded to every device
     whole, st = replicas[0].render(seed=4, sample_begin=1, sample_end=11)
     multi, sm = c.render_multi(replicas, seed=4, sample_begin=1, sample_end=11)
     assert (sm.samples, sm.closest_rays, sm.shadow_rays, sm.nan_samples) == (st.samples, st.closest_rays, st.shadow_rays, st.nan_samples)
