@@ -673,7 +673,7 @@ struct PoolStorage {
     uint64_t film_elems = 0;
     float* d_film_f32 = nullptr;      // staging of cray_render's host film
     unsigned persistent_blocks = 0;   // SMs x resident CTAs of the persistent traversal kernel
-    WideTuning tune{8, 8};
+    WideTuning tune{12, 8};
     unsigned shadow_blocks = 0;       // the any-hit instantiation needs fewer registers: its own occupancy
     unsigned long long* d_trace_counters = nullptr;  // {n, cursor} for the S3 entry points
     std::vector<cudaEvent_t> timers;                 // stage boundaries of every iteration of one render, reused across calls
