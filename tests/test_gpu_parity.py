@@ -343,3 +343,26 @@ def test_api_argument_errors():
     assert st.samples == gpu.width * gpu.height and np.isfinite(film).all()
     with pytest.raises(c.CrayError):
         c.Scene(hs, device=99)
+
+
+def test_duplicated_mesh_every_hit_is_a_tie():
+    """The same mesh listed twice: every triangle has an exact copy under another primitive index, so EVERY hit is an exact-t tie
+    and the winner is whichever copy the reference's traversal order reaches first.  Stresses the tie path of the wide
+    traversal (several ties per test round, ties against an earlier round's best) at scale."""
+    c.register_standin_mesh("objs/xyzrgb_dragon.obj", 0, 20001, 0)
+    text = scenes.dragon(width=96, height=64).replace(
+        "Mesh { file_name: 'objs/xyzrgb_dragon.obj', fallback_material: 'dragon' }",
+        "Mesh { file_name: 'objs/xyzrgb_dragon.obj', fallback_material: 'dragon' },\n    Mesh { file_name: 'objs/xyzrgb_dragon.obj', fallback_material: 'dragon' }")
+    hs = c.parse_scene(text, base_dir="/nonexistent")
+    assert hs.desc.n_triangles == 2 * 20001
+    gpu, orc = c.Scene(hs), o.OracleScene(hs)
+    xs, ys, ss = pixel_grid(gpu, 1)
+    rays = np.concatenate([orc.camera_rays(xs, ys, ss), random_rays([-120, -45, -60], [120, 60, 60], 200_000, seed=11)])
+    ref = orc.intersect(rays)
+    on_mesh = ref["prim"] >= 2  # primitives 0, 1 are the ground sphere and the light
+    assert on_mesh.sum() > 5_000
+    for mode, _ in MODES:
+        check_closest(gpu, orc, rays, mode)
+    film, st = gpu.render(seed=0, sample_begin=0, sample_end=2)
+    oref, counts = orc.render(gpu.width, gpu.height, seed=0, sample_begin=0, sample_end=2)
+    assert rel_mse(film, oref) <= 1e-8
