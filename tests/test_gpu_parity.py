@@ -366,3 +366,24 @@ def test_duplicated_mesh_every_hit_is_a_tie():
     film, st = gpu.render(seed=0, sample_begin=0, sample_end=2)
     oref, counts = orc.render(gpu.width, gpu.height, seed=0, sample_begin=0, sample_end=2)
     assert rel_mse(film, oref) <= 1e-8
+
+
+@pytest.mark.parametrize("lens", ["", ", lens_radius: 0.05, focal_distance: 4"])
+def test_orthographic_camera_and_thin_lens(lens):
+    """Camera::orthographic (camera.rs:105-129) and the square-aperture thin lens (:156-160) through render_pixel."""
+    text = scenes.test_scene(width=64, height=64)
+    start = text.index("camera: Perspective")
+    end = text.index("film:", start)
+    text = text[:start] + "camera: Orthographic { origin: Point(1.5, 1, -3), target: Point(1.5, 1, 0), up: Vector(0, 1, 0), " + text[end:]
+    text = text.replace("film: { width: 64, height: 64 }", "film: { width: 64, height: 64 }" + lens, 1)
+    hs = c.parse_scene(text)
+    assert hs.desc.camera.kind == 1 and (hs.desc.camera.lens_radius > 0) == bool(lens)
+    gpu, orc = c.Scene(hs), o.OracleScene(hs)
+    xs, ys, ss = pixel_grid(gpu, 1)
+    rays = orc.camera_rays(xs, ys, ss)
+    for mode, _ in MODES:
+        check_closest(gpu, orc, rays, mode)
+    got = gpu.estimate_Li(xs, ys, ss, seed=1)
+    ref, ok = orc.estimate_Li(xs, ys, ss, seed=1)
+    err = np.abs(got - ref) / (np.abs(ref) + 1e-3)
+    assert ok.all() and (err.max(axis=1) <= 1e-9).mean() >= 0.999
