@@ -387,3 +387,24 @@ def test_orthographic_camera_and_thin_lens(lens):
     ref, ok = orc.estimate_Li(xs, ys, ss, seed=1)
     err = np.abs(got - ref) / (np.abs(ref) + 1e-3)
     assert ok.all() and (err.max(axis=1) <= 1e-9).mean() >= 0.999
+
+
+def test_checkerboard_textures_colour_and_scalar():
+    """Texture::eval for Checkerboard (texture.rs:22-30) as a colour (reflectance) and as a scalar (Oren-Nayar sigma, plastic
+    roughness): the texture coordinates of spheres, disks and triangles all feed it."""
+    text = scenes.test_scene(width=80, height=80)
+    text = text.replace("white: Matte { reflectance: Color(1, 1, 1), sigma: 100 }",
+                        "white: Matte { reflectance: Checkerboard { a: Color(1, 1, 1), b: Color(0.2, 0.3, 0.4), scale: 900 }, sigma: Checkerboard { a: 0, b: 60, scale: 450 } }")
+    text = text.replace("red: Matte { reflectance: Color(1, 0, 0), sigma: 0 }",
+                        "red: Plastic { diffuse: Checkerboard { a: Color(1, 0, 0), b: Color(0, 0, 1), scale: 3 }, specular: Color(0.5, 0.5, 0.5), roughness: Checkerboard { a: 5, b: 0, scale: 2 } }")
+    assert text.count("Checkerboard") == 5
+    hs = c.parse_scene(text)
+    gpu, orc = c.Scene(hs), o.OracleScene(hs)
+    xs, ys, _ = pixel_grid(gpu, 1)
+    for sample in (0, 3):
+        ss = np.full_like(xs, sample)
+        ref, ok = orc.estimate_Li(xs, ys, ss, seed=2)
+        for mode, _ in MODES:
+            got = gpu.estimate_Li(xs, ys, ss, seed=2, mode=mode)
+            err = np.abs(got - ref) / (np.abs(ref) + 1e-3)
+            assert ok.all() and (err.max(axis=1) <= 1e-9).mean() >= 0.999
