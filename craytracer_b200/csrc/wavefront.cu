@@ -697,12 +697,14 @@ int ensure_pool(cray_scene* sc, uint32_t capacity) {
         if (const char* e = std::getenv("CRAY_BLOCKS_PER_SM")) ps->persistent_blocks = ps->shadow_blocks = (unsigned)(sms * std::max(1, std::atoi(e)));
     }
     if (ps->pool.capacity >= capacity) return CRAY_OK;
-    if (ps->slab) { cudaFree(ps->slab); ps->slab = nullptr; }
+    if (ps->slab) { cudaDeviceSynchronize(); cudaFree(ps->slab); ps->slab = nullptr; }  // (re-)allocation is rare: grow only
     const size_t n = capacity;
     const size_t n_f64 = 21, n_u32 = 8;
     const size_t bytes = n * (n_f64 * 8 + n_u32 * 4);
     CRAY_CUDA(cudaMalloc(&ps->slab, bytes));
+    // cleared before anyone can touch it, whichever stream the caller renders on
     CRAY_CUDA(cudaMemsetAsync(ps->slab, 0, bytes, sc->stream));
+    CRAY_CUDA(cudaStreamSynchronize(sc->stream));
     double* f = static_cast<double*>(ps->slab);
     Pool& p = ps->pool;
     double** fields[] = {&p.ox, &p.oy, &p.oz, &p.dx, &p.dy, &p.dz, &p.hit_t, &p.beta_r, &p.beta_g, &p.beta_b,

@@ -408,3 +408,28 @@ def test_checkerboard_textures_colour_and_scalar():
             got = gpu.estimate_Li(xs, ys, ss, seed=2, mode=mode)
             err = np.abs(got - ref) / (np.abs(ref) + 1e-3)
             assert ok.all() and (err.max(axis=1) <= 1e-9).mean() >= 0.999
+
+
+def test_device_entry_points_on_a_caller_stream():
+    """The *_device calls run on whatever stream the caller hands in (here a fresh non-default torch stream), including the very
+    first call on a new scene, which allocates the path pool."""
+    import torch
+    hs = c.parse_scene(scenes.materials(width=96, height=64))
+    gpu, orc = c.Scene(hs), o.OracleScene(hs)
+    side = torch.cuda.Stream()
+    film = torch.empty(gpu.height * gpu.width * 3, dtype=torch.float32, device="cuda")
+    with torch.cuda.stream(side):
+        st = gpu.render_device(film.data_ptr(), seed=0, sample_begin=0, sample_end=3, stream=side.cuda_stream)
+    side.synchronize()
+    ref, counts = orc.render(gpu.width, gpu.height, seed=0, sample_begin=0, sample_end=3)
+    assert (st.closest_rays, st.shadow_rays) == (int(counts[0]), int(counts[1]))
+    assert rel_mse(film.cpu().numpy().reshape(ref.shape), ref) <= 1e-8
+    rays = random_rays([-8, -1, -6], [12, 16, 16], 20_000, seed=5)
+    d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).cuda()
+    d_hits = torch.empty(len(rays) * 32, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    gpu.intersect_device(d_rays.data_ptr(), len(rays), d_hits.data_ptr(), mode=c.TRAVERSE_FAST, stream=side.cuda_stream)
+    side.synchronize()
+    hits = d_hits.cpu().numpy().view(c.HIT_DTYPE)
+    want = orc.intersect(rays)
+    assert np.array_equal(hits["prim"], want["prim"]) and np.array_equal(hits["t"], want["t"])
