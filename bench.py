@@ -219,9 +219,9 @@ def run_ours(args):
 
     hs, parse_s = build_host_scene(args)
     t0 = time.time()
-    scene = c.Scene(hs, device=local_rank)
+    scene = c.Scene(hs, device=local_rank, build=c.BUILD_EXACT | c.BUILD_FAST | (c.BUILD_F32 if args.mode == "f32" else 0))
     create_s = time.time() - t0
-    mode = c.TRAVERSE_EXACT if args.mode == "exact" else c.TRAVERSE_FAST
+    mode = {"exact": c.TRAVERSE_EXACT, "fast": c.TRAVERSE_FAST, "f32": c.TRAVERSE_F32}[args.mode]
     lo, hi = shard_samples(args.spp, rank, world)
     n_film = args.width * args.height * 3
     film = torch.zeros(n_film, dtype=torch.float32, device="cuda")
@@ -347,7 +347,8 @@ def main():
     ap.add_argument("--width", type=int, default=600)
     ap.add_argument("--height", type=int, default=400)
     ap.add_argument("--triangles", type=int, default=7_219_045)
-    ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--mode", default="fast", choices=["fast", "exact", "f32"],
+                    help="fast (default) and exact return the reference's hits bit for bit; f32 is the opt-in fast mode of SURVEY 8f n4")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of host work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

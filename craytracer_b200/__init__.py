@@ -12,11 +12,11 @@ import os
 import numpy as np
 
 from . import _abi
-from ._abi import (BUILD_EXACT, BUILD_FAST, CRAY_NO_HIT, HIT_DTYPE, RAY_DTYPE, SURFACE_DTYPE, TRAVERSE_EXACT, TRAVERSE_FAST, RenderStats, SceneDesc,
+from ._abi import (BUILD_EXACT, BUILD_F32, BUILD_FAST, CRAY_NO_HIT, HIT_DTYPE, RAY_DTYPE, SURFACE_DTYPE, TRAVERSE_EXACT, TRAVERSE_F32, TRAVERSE_FAST, RenderStats, SceneDesc,
                    SceneInfo)
 
 __all__ = ["ParserError", "CrayError", "HostScene", "Scene", "parse_scene", "load_scene", "make_rays", "tokenize", "parse_raw_value",
-           "register_standin_mesh", "write_exr", "render_multi", "TRAVERSE_EXACT", "TRAVERSE_FAST", "BUILD_EXACT", "BUILD_FAST", "CRAY_NO_HIT"]
+           "register_standin_mesh", "write_exr", "render_multi", "TRAVERSE_EXACT", "TRAVERSE_FAST", "TRAVERSE_F32", "BUILD_EXACT", "BUILD_FAST", "BUILD_F32", "CRAY_NO_HIT"]
 
 
 class CrayError(RuntimeError):

@@ -1,6 +1,6 @@
 """Command line of the reference (src/bin/craytracer.rs:321-374) over the B200 path:
 
-    python -m craytracer_b200 --scene scenes/dragon.cry [--output out.exr] [--seed 0] [--spp N] [--mode fast|exact] [--gpus N]
+    python -m craytracer_b200 --scene scenes/dragon.cry [--output out.exr] [--seed 0] [--spp N] [--mode fast|exact|f32] [--gpus N]
 
 Same flags as the reference's `Cli` (--scene/-s, --output, --seed, --preview); --preview is accepted and ignored (no window:
 SURVEY section 2 marks the minifb preview out of scope).  Meshes named by a scene are resolved against the scene file's
@@ -15,7 +15,7 @@ import time
 
 import numpy as np
 
-from . import Scene, TRAVERSE_EXACT, TRAVERSE_FAST, load_scene, render_multi, scenes, write_exr
+from . import BUILD_EXACT, BUILD_F32, BUILD_FAST, Scene, TRAVERSE_EXACT, TRAVERSE_F32, TRAVERSE_FAST, load_scene, render_multi, scenes, write_exr
 
 
 def find_base_dir(scene_path):
@@ -34,7 +34,7 @@ def main(argv=None):
     ap.add_argument("--preview", action="store_true", help="accepted for compatibility; ignored")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--spp", type=int, default=None, help="override the scene's num_samples")
-    ap.add_argument("--mode", choices=["fast", "exact"], default="fast")
+    ap.add_argument("--mode", choices=["fast", "exact", "f32"], default="fast")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--base-dir", default=None, help="directory mesh paths are resolved against")
     args = ap.parse_args(argv)
@@ -46,12 +46,12 @@ def main(argv=None):
     for w in hs.warnings:
         print(f"[WARN] {w}", file=sys.stderr)
     devices = list(range(max(1, args.gpus)))
-    gpu_scenes = Scene.create_multi(hs, devices)
+    gpu_scenes = Scene.create_multi(hs, devices, build=BUILD_EXACT | BUILD_FAST | (BUILD_F32 if args.mode == "f32" else 0))
     print(f"[INFO] Scene constructed in {time.time() - start:.3f}s", file=sys.stderr)
 
     sc0 = gpu_scenes[0]
     spp = args.spp if args.spp is not None else sc0.num_samples
-    mode = TRAVERSE_EXACT if args.mode == "exact" else TRAVERSE_FAST
+    mode = {"exact": TRAVERSE_EXACT, "fast": TRAVERSE_FAST, "f32": TRAVERSE_F32}[args.mode]
     t0 = time.time()
     film, st = render_multi(gpu_scenes, seed=args.seed, sample_begin=0, sample_end=spp, mode=mode)
     film = film / np.float32(max(spp, 1))  # pixels /= num_samples (craytracer.rs:253-259)

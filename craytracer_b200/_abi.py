@@ -20,8 +20,8 @@ TEX_CONSTANT, TEX_CHECKERBOARD, TEX_IMAGE = 0, 1, 2
 MAT_MATTE, MAT_GLASS, MAT_PLASTIC, MAT_METAL = 0, 1, 2, 3
 LIGHT_POINT, LIGHT_DISTANT, LIGHT_INFINITE, LIGHT_AREA = 0, 1, 2, 3
 CAMERA_PERSPECTIVE, CAMERA_ORTHOGRAPHIC = 0, 1
-BUILD_EXACT, BUILD_FAST = 1, 2
-TRAVERSE_EXACT, TRAVERSE_FAST = 0, 1
+BUILD_EXACT, BUILD_FAST, BUILD_F32 = 1, 2, 4
+TRAVERSE_EXACT, TRAVERSE_FAST, TRAVERSE_F32 = 0, 1, 2
 
 D3 = C.c_double * 3
 D2 = C.c_double * 2

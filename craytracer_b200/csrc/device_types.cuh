@@ -20,6 +20,18 @@ struct alignas(16) LeafPrim {
 };
 static_assert(sizeof(LeafPrim) == 80, "LeafPrim layout");
 
+// 48-byte f32 intersection record of the opt-in F32 mode, parallel to SceneView::wide_prims (same leaf slot):
+// the three vertices rounded to f32 -- triangles sharing a vertex share its rounded value, so the mesh stays closed.
+// Spheres and disks keep `kind` only; their test reads the f64 record of the same slot.
+struct alignas(16) Tri32 {
+    float v0[3], v1[3], v2[3];
+    uint32_t prim, kind;   // as LeafPrim
+    uint32_t _pad;
+};
+static_assert(sizeof(Tri32) == 48, "Tri32 layout");
+
+constexpr uint32_t kMaxAnalyticPre = 8;
+
 struct DiskXf {      // Shape::Disk, shape.rs:41-46
     Affine o2w;      // object_to_world.matrix
     Affine w2o;      // object_to_world.inverse == world_to_object.matrix
@@ -78,6 +90,9 @@ struct SceneView {
     const WideNode* wide_nodes;
     const LeafPrim* wide_prims;      // wide leaf order
     const uint32_t* rank_of_prim;    // primitive -> rank in the reference leaf order (exact-t tie breaking)
+    const Tri32* wide_tris32;        // F32 mode: f32 triangles in wide leaf order (null unless CRAY_BUILD_F32)
+    const uint32_t* analytic_slots;  // F32 mode: leaf slots of the spheres and disks, tested once per ray before the traversal ...
+    uint32_t n_analytic_pre;         // ... when there are at most kMaxAnalyticPre of them (else 0: they are tested where the BVH finds them)
     const DiskXf* disks;
     // shading
     const cray_primitive_desc* prims;

@@ -72,6 +72,21 @@ LeafPrim make_leaf_prim(const cray_scene_desc& d, uint32_t prim) {
     return lp;
 }
 
+// F32 mode record of the same leaf slot: v0, v1 = v0 + e1, v2 = v0 + e2 rounded to f32 (the sums reproduce the mesh's own
+// vertices to within an f64 ulp, so the f32 values of a shared vertex agree between its triangles)
+Tri32 make_tri32(const LeafPrim& lp) {
+    Tri32 t{};
+    t.prim = lp.prim;
+    t.kind = lp.kind;
+    if ((lp.kind & 0xFFu) == PRIM_TRIANGLE)
+        for (int a = 0; a < 3; ++a) {
+            t.v0[a] = (float)lp.d[a];
+            t.v1[a] = (float)(lp.d[a] + lp.d[3 + a]);
+            t.v2[a] = (float)(lp.d[a] + lp.d[6 + a]);
+        }
+    return t;
+}
+
 double shape_area(const cray_scene_desc& d, const cray_primitive_desc& p) {  // Shape::area shape.rs:504-514
     switch (p.shape_kind) {
         case CRAY_SHAPE_SPHERE: { const double r = d.spheres[p.shape_index].radius; return kPi * (r * r); }
@@ -173,6 +188,8 @@ struct HostBuild {
     RefBvh ref;
     WideBvh wide;
     std::vector<LeafPrim> bin_prims, wide_prims;
+    std::vector<Tri32> wide_tris32;
+    std::vector<uint32_t> analytic_slots;
     std::vector<uint32_t> rank_of_prim;
     std::vector<DiskXf> disks;
     std::vector<TriShade> tri_shade;
@@ -210,6 +227,8 @@ int build_host_side(const cray_scene_desc* d, uint32_t build_flags, HostBuild& h
     std::vector<LeafPrim>& wide_prims = hb.wide_prims;
     std::vector<uint32_t>& rank_of_prim = hb.rank_of_prim;
     bin_prims.resize(np); wide_prims.resize(wide.prim_order.size()); rank_of_prim.resize(np);
+    std::vector<Tri32>& wide_tris32 = hb.wide_tris32;
+    if (build_flags & CRAY_BUILD_F32) wide_tris32.resize(wide_prims.size());
     {
         const unsigned nt = std::max(1u, std::thread::hardware_concurrency());
         std::vector<std::thread> pool;
@@ -218,12 +237,16 @@ int build_host_side(const cray_scene_desc* d, uint32_t build_flags, HostBuild& h
                 bin_prims[i] = make_leaf_prim(*d, ref.prim_order[i]);
                 rank_of_prim[ref.prim_order[i]] = (uint32_t)i;
                 if (!wide_prims.empty()) wide_prims[i] = make_leaf_prim(*d, wide.prim_order[i]);
+                if (!wide_tris32.empty()) wide_tris32[i] = make_tri32(wide_prims[i]);
             }
         };
         for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t);
         work(0);
         for (auto& th : pool) th.join();
     }
+    for (size_t i = 0; i < hb.wide_tris32.size(); ++i)
+        if ((hb.wide_tris32[i].kind & 0xFFu) != PRIM_TRIANGLE && hb.analytic_slots.size() <= kMaxAnalyticPre) hb.analytic_slots.push_back((uint32_t)i);
+    if (hb.analytic_slots.size() > kMaxAnalyticPre) hb.analytic_slots.clear();
     timer.mark("leaf records");
     std::vector<DiskXf>& disks = hb.disks;
     disks.resize(d->n_disks);
@@ -371,6 +394,9 @@ int upload_scene(const HostBuild& hb, const cray_scene_desc* d, int device, cray
     UP(hb.bin_prims, v.bin_prims);
     UP(hb.wide.nodes, v.wide_nodes);
     UP(hb.wide_prims, v.wide_prims);
+    UP(hb.wide_tris32, v.wide_tris32);
+    UP(hb.analytic_slots, v.analytic_slots);
+    v.n_analytic_pre = (uint32_t)hb.analytic_slots.size();
     UP(hb.rank_of_prim, v.rank_of_prim);
     UP(hb.disks, v.disks);
     UP(hb.prims, v.prims);
@@ -469,6 +495,7 @@ int cray_scene_create_multi(const cray_scene_desc* d, const int* devices, int n,
     int rc = validate(d);
     if (rc != CRAY_OK) return rc;
     if (build_flags == 0) build_flags = CRAY_BUILD_EXACT | CRAY_BUILD_FAST;
+    if (build_flags & CRAY_BUILD_F32) build_flags |= CRAY_BUILD_FAST;  // the f32 records hang off the wide BVH's leaf slots
     build_flags |= CRAY_BUILD_EXACT;  // the binary tree also resolves exact-t ties for the fast mode
     rc = check_devices(devices, n);
     if (rc != CRAY_OK) return rc;

@@ -143,6 +143,33 @@ __device__ __noinline__ int analytic_candidate(const SceneView& s, const LeafPri
     return 0;
 }
 
+// ... and the any-hit test of a sphere or disk, out of line for the same reason (F32 mode)
+__device__ __noinline__ bool analytic_any(const SceneView& s, const LeafPrim& lp, V3 o, V3 dir, double ray_max) {
+    return leaf_prim_any(s, lp, o, dir, ray_max);
+}
+
+// F32 mode: the f64 triangle test of the parity mode for the rare f32 hit that needs confirming (prim_round_any32)
+__device__ __noinline__ bool triangle_any_f64(const SceneView& s, uint32_t slot, V3 o, V3 dir, double ray_max) {
+    const LeafPrim lp = load_leaf_prim(s.wide_prims + slot);
+    double t, u, v;
+    return triangle_hit(lp.d, o, dir, ray_max, t, u, v);
+}
+
+// Moeller-Trumbore without its range tests: t, u, v of the ray's crossing of the triangle's PLANE.  The F32 mode evaluates
+// the hit it found with this when the f64 test proper rejects it (a ray grazing an edge that f32 placed just inside).
+__device__ __forceinline__ bool triangle_eval_unchecked(const double* d9, V3 o, V3 dir, double& t, double& u, double& v) {
+    const V3 v0 = mk(d9[0], d9[1], d9[2]), e1 = mk(d9[3], d9[4], d9[5]), e2 = mk(d9[6], d9[7], d9[8]);
+    const V3 P = cross(dir, e2);
+    const double denominator = dot(P, e1);
+    if (denominator == 0.0) return false;
+    const V3 T = o - v0;
+    const V3 Q = cross(T, e1);
+    u = dot(P, T) / denominator;
+    v = dot(Q, dir) / denominator;
+    t = dot(Q, e2) / denominator;
+    return true;
+}
+
 // Wide-BVH closest-hit flavour.  0: rejected; 1: accepted (ray_max shrinks); 2: exact tie -- the strict `<` of
 // ray.rs:26 rejects it against the current ray_max, but its distance is bit-equal to it, so the reference keeps
 // whichever of the two primitives its own traversal reaches first.

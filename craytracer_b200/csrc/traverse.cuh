@@ -182,7 +182,8 @@ __device__ __forceinline__ void warp_begin_ray(WarpShared& ws, unsigned lane, V3
 
 // One interior node for one ray: pops the nearest pending child of the node group `ng`, tests its 8 quantised child boxes,
 // leaves the interior children hit in `ng` (octant ordered) and queues the primitives whose box was hit.
-__device__ __forceinline__ void node_step(const SceneView& s, WarpShared& ws, unsigned lane, const WideRay& r, uint2& ng, uint2* stack, int& sp) {
+template <class WS>
+__device__ __forceinline__ void node_step(const SceneView& s, WS& ws, unsigned lane, const WideRay& r, uint2& ng, uint2* stack, int& sp) {
     const uint32_t bit = 31u - __clz(ng.y);
     ng.y &= ~(1u << bit);
     const uint32_t slot = (bit - 24u) ^ r.octinv;
@@ -332,6 +333,219 @@ __device__ __forceinline__ void prim_round_any(const SceneView& s, WarpShared& w
         const V3 o = mk(ws.ox[owner], ws.oy[owner], ws.oz[owner]);
         const V3 dir = mk(ws.dx[owner], ws.dy[owner], ws.dz[owner]);
         if (leaf_prim_any(s, lp, o, dir, ws.tmax[owner])) ws.best[owner] = 1u;
+    }
+    const unsigned grp = __match_any_sync(FULL, act ? owner : 32u + lane);
+    if (act && lane == (unsigned)(__ffs(grp) - 1)) ws.pend[owner] -= __popc(grp);
+    __syncwarp();
+}
+
+// ---- F32 mode: the same traversal, triangles tested in f32 ---------------------------------------------------
+//
+// Watertight ray / triangle test of Woop, Benthin, Wald, "Watertight Ray/Triangle Intersection" (JCGT 2013): the vertices are
+// translated to the ray origin, sheared so that the ray runs along +z of a permuted frame, and the three 2-D edge functions
+// decide; a shared edge gets the same rounded products from both of its triangles (this file is compiled with --fmad=false), so
+// no ray slips between two triangles of a closed mesh, and an edge function that rounds to zero is re-evaluated in f64, where
+// the products of f32 values are exact.  The translation is done against the f64 origin split into an f32 head and an f32
+// remainder, (v - head) - rest, so that geometry near the origin is resolved relative to its distance from the origin and not
+// to the size of the scene's coordinates: what a ray leaving a surface needs.  Per ray (warp_begin_ray32): the permutation kz
+// and the shear Sx, Sy, Sz.  Both sides of a triangle are hit (the reference does not cull, shape.rs:227-248).
+//
+// The f64 ray itself is NOT kept in shared memory: the few tests that need it (spheres, disks, confirmations) read it again
+// from where the ray came from (Source::reload with the owner's ray id).  Shared memory not taken here stays L1 cache: at 8
+// CTAs per SM every KB per CTA moves the carve-out, and the traversal lives on its L1 hits.
+struct WarpShared32 {
+    float4 ra[32];        // origin head x, y, z | Sx
+    float4 rb[32];        // origin remainder x, y, z | Sy
+    float4 rc[32];        // Sz | kz (bits) | leaf slot of the triangle the ray leaves, CRAY_NO_HIT if none (bits) | closest distance so far
+    double tmax[32];      // closest-hit: distance of the best hit (exact f64 for spheres / disks); any-hit: the ray's max distance
+    float tmax32[32];     // slab-test bound
+    float tmin[32];       // smallest distance accepted (kEpsilon32, or the caller's allowance for a ray of unknown provenance)
+    float tsure[32];      // any-hit: an f32 distance beyond this is too close to the ray's end to be trusted (see prim_round_any32)
+    uint32_t best[32];
+    uint32_t pend[32];
+    uint32_t tail;
+    uint32_t _pad[3];
+    uint32_t queue[kQueue];
+};
+
+constexpr float kEpsilon32 = 1e-9f;   // Ray::contains_distance's lower bound (ray.rs:26)
+
+// S3 rays carry no record of the surface they start on, and in f32 a triangle lies up to an ulp of its coordinates off its f64
+// plane: distances below 2^-19 of the origin's largest coordinate (in units of the direction's largest component) are taken for
+// the ray's own surface.  The wavefront knows the triangle a ray leaves and skips exactly that one instead.
+__device__ __forceinline__ float f32_unknown_origin_tmin(V3 o, V3 dir) {
+    const float om = fmaxf(fmaxf(fabsf((float)o.x), fabsf((float)o.y)), fabsf((float)o.z));
+    const float dm = fmaxf(fmaxf(fabsf((float)dir.x), fabsf((float)dir.y)), fabsf((float)dir.z));
+    return fmaxf(kEpsilon32, 1.9073486e-6f * om / fmaxf(dm, 1e-30f));
+}
+
+// Closest hit with a finite max distance (S3 rays only): pulled in by 2^-18 relative, so that a surface AT the end of the ray is
+// not found a few ulps in front of it.  (Shadow rays get the exact treatment, see prim_round_any32.)
+__device__ __forceinline__ float f32_ray_max(double ray_max) {
+    const float m = __double2float_rd(ray_max);
+    return isinf(m) ? m : __fmul_rd(m, 1.0f - 3.8146973e-6f);
+}
+
+template <bool ANY>
+__device__ __forceinline__ void warp_begin_ray32(WarpShared32& ws, unsigned lane, V3 o, V3 dir, double ray_max, uint32_t best_init, uint32_t self_slot, float tmin) {
+    ws.tmin[lane] = tmin;
+    ws.tmax[lane] = ray_max;
+    ws.tmax32[lane] = slab_tmax(ray_max);
+    ws.best[lane] = best_init;
+    ws.pend[lane] = 0u;
+    const float hx = (float)o.x, hy = (float)o.y, hz = (float)o.z;
+    const float fx = (float)dir.x, fy = (float)dir.y, fz = (float)dir.z;
+    const float ax = fabsf(fx), ay = fabsf(fy), az = fabsf(fz);
+    const uint32_t kz = ax > ay ? (ax > az ? 0u : 2u) : (ay > az ? 1u : 2u);
+    // (kx, ky, kz) is a cyclic shift of (x, y, z)
+    const float dk = kz == 0u ? fx : (kz == 1u ? fy : fz);
+    const float dkx = kz == 0u ? fy : (kz == 1u ? fz : fx);
+    const float dky = kz == 0u ? fz : (kz == 1u ? fx : fy);
+    ws.ra[lane] = make_float4(hx, hy, hz, dkx / dk);
+    ws.rb[lane] = make_float4((float)(o.x - (double)hx), (float)(o.y - (double)hy), (float)(o.z - (double)hz), dky / dk);
+    const float full = __double2float_ru(ray_max);
+    ws.tsure[lane] = __fmul_rd(full, 0.9990234375f);  // 1 - 2^-10 (+inf stays +inf: every distance is trusted)
+    ws.rc[lane] = make_float4(1.0f / dk, __uint_as_float(kz), __uint_as_float(self_slot), ANY ? full : f32_ray_max(ray_max));
+}
+
+__device__ __forceinline__ float& closest32(WarpShared32& ws, uint32_t owner) { return ws.rc[owner].w; }
+
+struct Tri32Regs { float4 a, b, c; };   // v0.xyz v1.x | v1.yz v2.xy | v2.z prim kind pad
+__device__ __forceinline__ Tri32Regs load_tri32(const Tri32* p) {
+    const float4* src = reinterpret_cast<const float4*>(p);
+    Tri32Regs r;
+    r.a = __ldg(src); r.b = __ldg(src + 1); r.c = __ldg(src + 2);
+    return r;
+}
+
+// true iff the ray of `owner` crosses the triangle; t = distance along the (un-normalised) direction
+__device__ __forceinline__ bool tri32_hit(const Tri32Regs& tr, const WarpShared32& ws, uint32_t owner, float& t) {
+    const float4 ra = ws.ra[owner], rb = ws.rb[owner], rc = ws.rc[owner];
+    const uint32_t kz = __float_as_uint(rc.y);
+    // ray-relative vertices
+    const float a0 = (tr.a.x - ra.x) - rb.x, a1 = (tr.a.y - ra.y) - rb.y, a2 = (tr.a.z - ra.z) - rb.z;
+    const float b0 = (tr.a.w - ra.x) - rb.x, b1 = (tr.b.x - ra.y) - rb.y, b2 = (tr.b.y - ra.z) - rb.z;
+    const float c0 = (tr.b.z - ra.x) - rb.x, c1 = (tr.b.w - ra.y) - rb.y, c2 = (tr.c.x - ra.z) - rb.z;
+    // permuted: (kx, ky, kz) = kz + 1, kz + 2, kz
+    const float akx = kz == 0u ? a1 : (kz == 1u ? a2 : a0), aky = kz == 0u ? a2 : (kz == 1u ? a0 : a1), akz = kz == 0u ? a0 : (kz == 1u ? a1 : a2);
+    const float bkx = kz == 0u ? b1 : (kz == 1u ? b2 : b0), bky = kz == 0u ? b2 : (kz == 1u ? b0 : b1), bkz = kz == 0u ? b0 : (kz == 1u ? b1 : b2);
+    const float ckx = kz == 0u ? c1 : (kz == 1u ? c2 : c0), cky = kz == 0u ? c2 : (kz == 1u ? c0 : c1), ckz = kz == 0u ? c0 : (kz == 1u ? c1 : c2);
+    const float Sx = ra.w, Sy = rb.w, Sz = rc.x;
+    const float Ax = akx - Sx * akz, Ay = aky - Sy * akz;
+    const float Bx = bkx - Sx * bkz, By = bky - Sy * bkz;
+    const float Cx = ckx - Sx * ckz, Cy = cky - Sy * ckz;
+    float U = Cx * By - Cy * Bx, V = Ax * Cy - Ay * Cx, W = Bx * Ay - By * Ax;
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {  // on an edge to f32 precision: the products are exact in f64
+        U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+        V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+        W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    const float det = U + V + W;
+    if (det == 0.0f) return false;
+    const float T = U * (Sz * akz) + V * (Sz * bkz) + W * (Sz * ckz);
+    t = T / det;
+    return true;
+}
+
+// A scene's few spheres and disks (dragon.cry: the ground sphere and the light disk, which nearly every ray's traversal runs
+// into) are tested once per ray, in f64, while the ray is still in registers -- the closest of them bounds the traversal from
+// its first node on -- and skipped where the BVH finds them.
+template <bool ANY>
+__device__ __forceinline__ void pretest_analytic32(const SceneView& s, WarpShared32& ws, unsigned lane, V3 o, V3 dir, double ray_max) {
+    for (uint32_t k = 0; k < s.n_analytic_pre; ++k) {
+        const uint32_t slot = s.analytic_slots[k];
+        const LeafPrim lp = load_leaf_prim(s.wide_prims + slot);
+        if constexpr (ANY) {
+            if (analytic_any(s, lp, o, dir, ray_max)) { ws.best[lane] = 1u; break; }
+        } else {
+            double cand = (double)closest32(ws, lane);
+            if (analytic_candidate(s, lp, o, dir, cand, false) == 1) {
+                closest32(ws, lane) = __double2float_rd(cand);
+                ws.best[lane] = slot;
+                ws.tmax[lane] = cand;
+                ws.tmax32[lane] = slab_tmax(cand);
+            }
+        }
+    }
+}
+
+// Closest-hit round of the F32 mode: as prim_round_closest, with the closest distance kept as an f32 bit pattern.  Equal
+// distances: the lowest lane of a round wins, a later round's equal distance replaces it (no reference order in this mode).
+template <class Source>
+__device__ __forceinline__ void prim_round_closest32(const SceneView& s, WarpShared32& ws, unsigned lane, uint32_t head, uint32_t count, const Source& src, uint32_t id) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const bool act = lane < count;
+    const uint32_t e = act ? ws.queue[(head + lane) & (kQueue - 1u)] : 0u;
+    const uint32_t owner = e >> kSlotBits, slot = e & kSlotMask;
+    const uint32_t owner_id = __shfl_sync(FULL, id, owner);
+    bool hit = false;
+    float t32 = 0.0f;
+    double t64 = 0.0;
+    if (act) {
+        const Tri32Regs tr = load_tri32(s.wide_tris32 + slot);
+        if ((__float_as_uint(tr.c.z) & 0xFFu) == PRIM_TRIANGLE) {
+            float t;
+            if (slot != __float_as_uint(ws.rc[owner].z) && tri32_hit(tr, ws, owner, t) && t > ws.tmin[owner] && t < closest32(ws, owner)) {
+                hit = true; t32 = t; t64 = (double)t;
+            }
+        } else if (s.n_analytic_pre == 0u) {  // spheres and disks (not pre-tested): the f64 test of the parity mode on the f64 ray
+            const LeafPrim lp = load_leaf_prim(s.wide_prims + slot);
+            double cand = (double)closest32(ws, owner), unused;
+            V3 o, dir;
+            src.reload(owner_id, o, dir, unused);
+            if (analytic_candidate(s, lp, o, dir, cand, false) == 1) {
+                hit = true; t64 = cand; t32 = __double2float_rd(cand);
+            }
+        }
+    }
+    if (hit) atomicMin(reinterpret_cast<unsigned*>(&closest32(ws, owner)), __float_as_uint(t32));
+    __syncwarp();
+    const unsigned grp = __match_any_sync(FULL, act ? owner : 32u + lane);
+    const bool win = hit && closest32(ws, owner) == t32;
+    const unsigned wins = __ballot_sync(FULL, win) & grp;
+    if (win && lane == (unsigned)(__ffs(wins) - 1)) {
+        ws.best[owner] = slot;
+        ws.tmax[owner] = t64;
+        ws.tmax32[owner] = slab_tmax(t64);
+    }
+    if (act && lane == (unsigned)(__ffs(grp) - 1)) ws.pend[owner] -= __popc(grp);
+    __syncwarp();
+}
+
+// Any-hit round of the F32 mode.  A shadow ray ends 1e-9 short of its light sample (light.rs:124), and that sample lies ON a
+// surface -- the light's own triangle for a mesh light -- whose f32 distance is uncertain by a few ulps divided by the cosine of
+// the angle of incidence.  An f32 hit in the last 2^-10 of the ray is therefore confirmed by the f64 test of the parity mode
+// against the exact max distance (out of line; a fraction of a percent of the tests), everything nearer is taken as it is.
+template <class Source>
+__device__ __forceinline__ void prim_round_any32(const SceneView& s, WarpShared32& ws, unsigned lane, uint32_t head, uint32_t count, const Source& src, uint32_t id) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const bool act = lane < count;
+    const uint32_t e = act ? ws.queue[(head + lane) & (kQueue - 1u)] : 0u;
+    const uint32_t owner = e >> kSlotBits, slot = e & kSlotMask;
+    const uint32_t owner_id = __shfl_sync(FULL, id, owner);
+    if (act && ws.best[owner] == 0u) {
+        const Tri32Regs tr = load_tri32(s.wide_tris32 + slot);
+        bool occ;
+        if ((__float_as_uint(tr.c.z) & 0xFFu) == PRIM_TRIANGLE) {
+            float t;
+            occ = slot != __float_as_uint(ws.rc[owner].z) && tri32_hit(tr, ws, owner, t) && t > ws.tmin[owner] && t < closest32(ws, owner);
+            if (occ && t > ws.tsure[owner]) {
+                V3 o, dir;
+                double ray_max;
+                src.reload(owner_id, o, dir, ray_max);
+                occ = triangle_any_f64(s, slot, o, dir, ray_max);
+            }
+        } else if (s.n_analytic_pre == 0u) {
+            const LeafPrim lp = load_leaf_prim(s.wide_prims + slot);
+            V3 o, dir;
+            double ray_max;
+            src.reload(owner_id, o, dir, ray_max);
+            occ = analytic_any(s, lp, o, dir, ray_max);
+        } else {
+            occ = false;
+        }
+        if (occ) ws.best[owner] = 1u;
     }
     const unsigned grp = __match_any_sync(FULL, act ? owner : 32u + lane);
     if (act && lane == (unsigned)(__ffs(grp) - 1)) ws.pend[owner] -= __popc(grp);

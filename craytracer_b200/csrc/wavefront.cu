@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "scene_device.hpp"
@@ -58,6 +59,7 @@ struct Job {
     double* out_rgb;            // per-sample radiance (S2), or null
     const uint32_t* sobol;
     int exact;                  // traversal mode
+    int f32;                    // F32 mode: hit_t is an f32-precision distance, the hit is re-evaluated in f64 when shaded
 };
 
 struct Counters {
@@ -75,6 +77,12 @@ __device__ __forceinline__ uint32_t st_bounces(uint32_t s) { return (s >> 8) & 0
 
 struct ExtendSource {  // queued path rays -> Pool::hit_*
     Pool p;
+    // the f64 ray of path slot `i` again (F32 mode: the tests of spheres and disks)
+    __device__ __forceinline__ void reload(uint32_t i, V3& o, V3& d, double& ray_max) const {
+        o = mk(p.ox[i], p.oy[i], p.oz[i]);
+        d = mk(p.dx[i], p.dy[i], p.dz[i]);
+        ray_max = inf_f64();
+    }
     __device__ __forceinline__ uint32_t load(uint64_t idx, V3& o, V3& d, double& ray_max) const {
         const uint32_t i = p.extend_queue[idx];
         o = mk(p.ox[i], p.oy[i], p.oz[i]);
@@ -82,6 +90,9 @@ struct ExtendSource {  // queued path rays -> Pool::hit_*
         ray_max = inf_f64();
         return i;
     }
+    // F32 mode: the leaf slot the ray leaves -- the hit of the path's previous vertex, CRAY_NO_HIT for a camera ray (k_generate)
+    __device__ __forceinline__ uint32_t self_slot(uint32_t i) const { return p.hit_slot[i]; }
+    __device__ __forceinline__ float t_min32(V3, V3) const { return kEpsilon32; }
     __device__ __forceinline__ void store_closest(const SceneView&, uint32_t i, uint32_t slot, double t) const {
         p.hit_slot[i] = slot;
         p.hit_t[i] = t;
@@ -91,6 +102,11 @@ struct ExtendSource {  // queued path rays -> Pool::hit_*
 
 struct ShadowSource {  // queued shadow rays -> L += contribution when unoccluded (path_integrator.rs:141-163)
     Pool p;
+    __device__ __forceinline__ void reload(uint32_t i, V3& o, V3& d, double& ray_max) const {
+        o = mk(p.ox[i], p.oy[i], p.oz[i]);
+        d = mk(p.sdx[i], p.sdy[i], p.sdz[i]);
+        ray_max = p.smax[i];
+    }
     __device__ __forceinline__ uint32_t load(uint64_t idx, V3& o, V3& d, double& ray_max) const {
         const uint32_t i = p.shadow_queue[idx];
         o = mk(p.ox[i], p.oy[i], p.oz[i]);
@@ -98,6 +114,8 @@ struct ShadowSource {  // queued shadow rays -> L += contribution when unocclude
         ray_max = p.smax[i];
         return i;
     }
+    __device__ __forceinline__ uint32_t self_slot(uint32_t i) const { return p.hit_slot[i]; }
+    __device__ __forceinline__ float t_min32(V3, V3) const { return kEpsilon32; }
     __device__ __forceinline__ void store_closest(const SceneView&, uint32_t, uint32_t, double) const {}
     __device__ __forceinline__ void store_any(uint32_t i, bool occluded) const {
         if (!occluded) { p.L_r[i] += p.sc_r[i]; p.L_g[i] += p.sc_g[i]; p.L_b[i] += p.sc_b[i]; }
@@ -105,8 +123,10 @@ struct ShadowSource {  // queued shadow rays -> L += contribution when unocclude
 };
 
 // `h.u, h.v` are only consulted when `have_uv`; otherwise a triangle's barycentrics are re-derived from (slot, t).
+// `f32`: F32 mode, h.t has f32 precision -- the triangle found is evaluated again in f64 (t, u, v of its plane if the f64 test
+// itself rejects a grazing hit).
 __device__ __forceinline__ void write_hit(const SceneView& s, const LeafPrim* prims, const cray_ray& r, Hit h, bool have_uv, bool found, uint64_t i,
-                                          cray_hit* hits, cray_surface* surf) {
+                                          cray_hit* hits, cray_surface* surf, bool f32 = false) {
     cray_hit out;
     out._pad = 0;
     cray_surface sf;
@@ -116,8 +136,9 @@ __device__ __forceinline__ void write_hit(const SceneView& s, const LeafPrim* pr
         const LeafPrim lp = load_leaf_prim(prims + h.slot);
         const bool tri = (lp.kind & 0xFFu) == PRIM_TRIANGLE;
         if (tri && !have_uv) {
-            double t2;
-            triangle_eval(lp.d, o, d, t2, h.u, h.v);
+            double t2 = h.t;
+            if (!triangle_eval(lp.d, o, d, t2, h.u, h.v) && f32) triangle_eval_unchecked(lp.d, o, d, t2, h.u, h.v);
+            if (f32) h.t = t2;
         }
         V3 loc, nrm;
         double tu, tv;
@@ -142,6 +163,15 @@ struct RayArraySource {  // S3: caller-provided cray_ray records
     cray_hit* hits;
     cray_surface* surf;
     uint8_t* occluded;
+    bool f32;
+    __device__ __forceinline__ void reload(uint32_t i, V3& o, V3& d, double& ray_max) const {
+        const cray_ray r = rays[i];
+        o = mk(r.origin[0], r.origin[1], r.origin[2]);
+        d = mk(r.direction[0], r.direction[1], r.direction[2]);
+        ray_max = r.max_distance;
+    }
+    __device__ __forceinline__ uint32_t self_slot(uint32_t) const { return CRAY_NO_HIT; }
+    __device__ __forceinline__ float t_min32(V3 o, V3 d) const { return f32_unknown_origin_tmin(o, d); }
     __device__ __forceinline__ uint32_t load(uint64_t idx, V3& o, V3& d, double& ray_max) const {
         const cray_ray r = rays[idx];
         o = mk(r.origin[0], r.origin[1], r.origin[2]);
@@ -152,7 +182,7 @@ struct RayArraySource {  // S3: caller-provided cray_ray records
     __device__ __forceinline__ void store_closest(const SceneView& s, uint32_t i, uint32_t slot, double t) const {
         Hit h;
         h.slot = slot; h.t = t; h.u = 0.0; h.v = 0.0;
-        write_hit(s, s.wide_prims, rays[i], h, false, slot != CRAY_NO_HIT, i, hits, surf);
+        write_hit(s, s.wide_prims, rays[i], h, false, slot != CRAY_NO_HIT, i, hits, surf, f32);
     }
     __device__ __forceinline__ void store_any(uint32_t i, bool occ) const { occluded[i] = occ ? 1 : 0; }
 };
@@ -179,6 +209,10 @@ constexpr int kWideMinBlocks = CRAY_WIDE_MIN_BLOCKS;
 #define CRAY_WIDE_MIN_BLOCKS_ANY 8
 #endif
 constexpr int kWideMinBlocksAny = CRAY_WIDE_MIN_BLOCKS_ANY;   // the any-hit instantiation carries less state   // CTAs of 128 threads per SM the register allocation is held to
+#ifndef CRAY_WIDE_MIN_BLOCKS_F32
+#define CRAY_WIDE_MIN_BLOCKS_F32 8
+#endif
+constexpr int kWideMinBlocksF32 = CRAY_WIDE_MIN_BLOCKS_F32;   // F32 mode: no f64 triangle test to hold registers for
 
 enum : int { LANE_IDLE = 0, LANE_LIVE = 1, LANE_DRAIN = 2 };
 
@@ -195,10 +229,11 @@ __device__ unsigned long long g_wide_stats[2][8];
 #define WIDE_STAT(k, v)
 #endif
 
-template <bool ANY, class Source>
-__global__ void __launch_bounds__(128, ANY ? kWideMinBlocksAny : kWideMinBlocks) k_wide_persistent(SceneView s, Source src, const unsigned long long* __restrict__ n_ptr, unsigned long long* cursor, WideTuning tune) {
-    __shared__ WarpShared shared[4];
-    WarpShared& ws = shared[threadIdx.x >> 5];
+template <bool ANY, class Source, bool F32 = false>
+__global__ void __launch_bounds__(128, F32 ? kWideMinBlocksF32 : (ANY ? kWideMinBlocksAny : kWideMinBlocks)) k_wide_persistent(SceneView s, Source src, const unsigned long long* __restrict__ n_ptr, unsigned long long* cursor, WideTuning tune) {
+    using WS = std::conditional_t<F32, WarpShared32, WarpShared>;
+    __shared__ WS shared[4];
+    WS& ws = shared[threadIdx.x >> 5];
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long n = *n_ptr;
@@ -233,7 +268,12 @@ __global__ void __launch_bounds__(128, ANY ? kWideMinBlocksAny : kWideMinBlocks)
                     double ray_max;
                     id = src.load(idx, o, d, ray_max);
                     r = make_wide_ray(o, d, ray_max);
-                    warp_begin_ray(ws, lane, o, d, ray_max, ANY ? 0u : CRAY_NO_HIT);
+                    if constexpr (F32) {
+                        warp_begin_ray32<ANY>(ws, lane, o, d, ray_max, ANY ? 0u : CRAY_NO_HIT, src.self_slot(id), src.t_min32(o, d));
+                        pretest_analytic32<ANY>(s, ws, lane, o, d, ray_max);
+                        r.tmax = ws.tmax32[lane];
+                    }
+                    else warp_begin_ray(ws, lane, o, d, ray_max, ANY ? 0u : CRAY_NO_HIT);
                     ng = make_uint2(0u, 0x80000000u);  // the root, as a one-child node group
                     sp = 0;
                     state = LANE_LIVE;
@@ -252,6 +292,9 @@ __global__ void __launch_bounds__(128, ANY ? kWideMinBlocksAny : kWideMinBlocks)
             if (!(ng.y & 0xFF000000u) && sp > 0) ng = stack[--sp];
             stepping = (ng.y & 0xFF000000u) != 0u;
             if (stepping) node_step(s, ws, lane, r, ng, stack, sp);
+            // a node group with nothing left to visit is replaced from the stack right away: the (local-memory) load has the
+            // rest of the iteration to arrive instead of stalling the next node step
+            if (!(ng.y & 0xFF000000u) && sp > 0) ng = stack[--sp];
         }
 #if CRAY_WIDE_STATS
         {
@@ -269,7 +312,9 @@ __global__ void __launch_bounds__(128, ANY ? kWideMinBlocksAny : kWideMinBlocks)
             const unsigned waiting = __ballot_sync(FULL, state != LANE_IDLE && !node_work);
             while (count >= 32u || (count > 0u && (node_lanes == 0u || __popc(waiting) >= tune.wait_lanes))) {
                 const uint32_t take = count < 32u ? count : 32u;
-                if constexpr (ANY) prim_round_any(s, ws, lane, head, take);
+                if constexpr (F32 && ANY) prim_round_any32(s, ws, lane, head, take, src, id);
+                else if constexpr (F32) prim_round_closest32(s, ws, lane, head, take, src, id);
+                else if constexpr (ANY) prim_round_any(s, ws, lane, head, take);
                 else prim_round_closest(s, ws, lane, head, take);
                 head += take;
                 count -= take;
@@ -407,6 +452,7 @@ __global__ void __launch_bounds__(256) k_generate(SceneView s, Pool p, Job job, 
             p.beta_r[i] = 1.0; p.beta_g[i] = 1.0; p.beta_b[i] = 1.0;
             p.L_r[i] = 0.0; p.L_g[i] = 0.0; p.L_b[i] = 0.0;
             p.prev_bsdf_pdf[i] = 0.0;
+            p.hit_slot[i] = CRAY_NO_HIT;  // a camera ray leaves no surface (F32 mode's self-intersection rule)
             p.id[i] = (uint32_t)id;
             p.pixel[i] = x + y * s.camera.width;
             p.hash[i] = smp.hash;
@@ -540,11 +586,13 @@ __global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(Scen
     const LeafPrim lp = load_leaf_prim((job.exact ? s.bin_prims : s.wide_prims) + slot);
     V3 location, normal;
     double tu, tv;
-    const double hit_t = p.hit_t[i];
+    double hit_t = p.hit_t[i];
     double bu = 0.0, bv = 0.0;
     if ((lp.kind & 0xFFu) == PRIM_TRIANGLE) {  // the barycentrics the traversal computed for this hit (same code, same bits)
-        double t2;
-        triangle_eval(lp.d, ro, rd, t2, bu, bv);
+        double t2 = hit_t;
+        // F32 mode: the f32 traversal chose the triangle, t / u / v are the f64 values of that choice
+        if (!triangle_eval(lp.d, ro, rd, t2, bu, bv) && job.f32) triangle_eval_unchecked(lp.d, ro, rd, t2, bu, bv);
+        if (job.f32) hit_t = t2;
     }
     // Primitive's material / light binding: triangles carry it in the first sector of their shading record
     int32_t material_index, area_light;
@@ -675,6 +723,7 @@ struct PoolStorage {
     unsigned persistent_blocks = 0;   // SMs x resident CTAs of the persistent traversal kernel
     WideTuning tune{12, 8};
     unsigned shadow_blocks = 0;       // the any-hit instantiation needs fewer registers: its own occupancy
+    unsigned f32_blocks = 0, f32_shadow_blocks = 0;  // F32 mode instantiations
     unsigned long long* d_trace_counters = nullptr;  // {n, cursor} for the S3 entry points
     std::vector<cudaEvent_t> timers;                 // stage boundaries of every iteration of one render, reused across calls
 };
@@ -692,9 +741,13 @@ int ensure_pool(cray_scene* sc, uint32_t capacity) {
         ps->persistent_blocks = (unsigned)(sms * std::max(per_sm, 1));
         CRAY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wide_persistent<true, ShadowSource>, 128, 0));
         ps->shadow_blocks = (unsigned)(sms * std::max(per_sm, 1));
+        CRAY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wide_persistent<false, ExtendSource, true>, 128, 0));
+        ps->f32_blocks = (unsigned)(sms * std::max(per_sm, 1));
+        CRAY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wide_persistent<true, ShadowSource, true>, 128, 0));
+        ps->f32_shadow_blocks = (unsigned)(sms * std::max(per_sm, 1));
         if (const char* e = std::getenv("CRAY_REFILL_LANES")) ps->tune.refill_lanes = std::max(1, std::min(32, std::atoi(e)));
         if (const char* e = std::getenv("CRAY_WAIT_LANES")) ps->tune.wait_lanes = std::max(1, std::min(33, std::atoi(e)));
-        if (const char* e = std::getenv("CRAY_BLOCKS_PER_SM")) ps->persistent_blocks = ps->shadow_blocks = (unsigned)(sms * std::max(1, std::atoi(e)));
+        if (const char* e = std::getenv("CRAY_BLOCKS_PER_SM")) ps->persistent_blocks = ps->shadow_blocks = ps->f32_blocks = ps->f32_shadow_blocks = (unsigned)(sms * std::max(1, std::atoi(e)));
     }
     if (ps->pool.capacity >= capacity) return CRAY_OK;
     if (ps->slab) { cudaDeviceSynchronize(); cudaFree(ps->slab); ps->slab = nullptr; }  // (re-)allocation is rare: grow only
@@ -757,12 +810,14 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
         CRAY_CUDA(cudaEventRecord(gen_done, stream));
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 1], stream));
         if (job.exact) k_extend_exact<<<g128, 128, 0, stream>>>(sc->view, pool, &dc->n_extend);
+        else if (job.f32) k_wide_persistent<false, ExtendSource, true><<<ps->f32_blocks, 128, 0, stream>>>(sc->view, ExtendSource{pool}, &dc->n_extend, &dc->extend_cursor, ps->tune);
         else k_wide_persistent<false, ExtendSource><<<gp, 128, 0, stream>>>(sc->view, ExtendSource{pool}, &dc->n_extend, &dc->extend_cursor, ps->tune);
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 2], stream));
         k_shade<<<(capacity + kShadeThreads - 1) / kShadeThreads, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 3], stream));
         // at most one shadow ray per shaded vertex; the queue length lives on the device
         if (job.exact) k_shadow_exact<<<g128, 128, 0, stream>>>(sc->view, pool, &dc->n_shadow);
+        else if (job.f32) k_wide_persistent<true, ShadowSource, true><<<ps->f32_shadow_blocks, 128, 0, stream>>>(sc->view, ShadowSource{pool}, &dc->n_shadow, &dc->shadow_cursor, ps->tune);
         else k_wide_persistent<true, ShadowSource><<<gs, 128, 0, stream>>>(sc->view, ShadowSource{pool}, &dc->n_shadow, &dc->shadow_cursor, ps->tune);
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 4], stream));
         launches += 4;
@@ -803,7 +858,8 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
 
 int check_mode(const cray_scene* sc, int mode) {
     if (!sc) { set_error("null scene"); return CRAY_E_INVALID; }
-    if (mode != CRAY_TRAVERSE_EXACT && mode != CRAY_TRAVERSE_FAST) { set_error("unknown traversal mode"); return CRAY_E_INVALID; }
+    if (mode != CRAY_TRAVERSE_EXACT && mode != CRAY_TRAVERSE_FAST && mode != CRAY_TRAVERSE_F32) { set_error("unknown traversal mode"); return CRAY_E_INVALID; }
+    if (mode == CRAY_TRAVERSE_F32 && !(sc->build_flags & CRAY_BUILD_F32)) { set_error("scene was created without CRAY_BUILD_F32"); return CRAY_E_INVALID; }
     if (mode == CRAY_TRAVERSE_FAST && !(sc->build_flags & CRAY_BUILD_FAST)) { set_error("scene was created without CRAY_BUILD_FAST"); return CRAY_E_INVALID; }
     return CRAY_OK;
 }
@@ -857,9 +913,13 @@ static int launch_trace(cray_scene* sc, int mode, bool any, const cray_ray* d_ra
         if (!ps->d_trace_counters) CRAY_CUDA(cudaMalloc(&ps->d_trace_counters, 2 * sizeof(unsigned long long)));
         const unsigned long long init[2] = {n, 0ull};
         CRAY_CUDA(cudaMemcpyAsync(ps->d_trace_counters, init, sizeof(init), cudaMemcpyHostToDevice, stream));
-        const RayArraySource src{d_rays, d_hits, d_surf, d_occluded};
-        const unsigned blocks = (unsigned)std::min<uint64_t>(any ? ps->shadow_blocks : ps->persistent_blocks, (n + 127) / 128);
-        if (any) k_wide_persistent<true, RayArraySource><<<blocks, 128, 0, stream>>>(sc->view, src, ps->d_trace_counters, ps->d_trace_counters + 1, ps->tune);
+        const bool f32 = mode == CRAY_TRAVERSE_F32;
+        const RayArraySource src{d_rays, d_hits, d_surf, d_occluded, f32};
+        const unsigned resident = f32 ? (any ? ps->f32_shadow_blocks : ps->f32_blocks) : (any ? ps->shadow_blocks : ps->persistent_blocks);
+        const unsigned blocks = (unsigned)std::min<uint64_t>(resident, (n + 127) / 128);
+        if (f32 && any) k_wide_persistent<true, RayArraySource, true><<<blocks, 128, 0, stream>>>(sc->view, src, ps->d_trace_counters, ps->d_trace_counters + 1, ps->tune);
+        else if (f32) k_wide_persistent<false, RayArraySource, true><<<blocks, 128, 0, stream>>>(sc->view, src, ps->d_trace_counters, ps->d_trace_counters + 1, ps->tune);
+        else if (any) k_wide_persistent<true, RayArraySource><<<blocks, 128, 0, stream>>>(sc->view, src, ps->d_trace_counters, ps->d_trace_counters + 1, ps->tune);
         else k_wide_persistent<false, RayArraySource><<<blocks, 128, 0, stream>>>(sc->view, src, ps->d_trace_counters, ps->d_trace_counters + 1, ps->tune);
     }
     CRAY_CUDA(cudaGetLastError());
@@ -949,6 +1009,7 @@ int cray_estimate_li(cray_scene* sc, int mode, uint64_t seed, const uint32_t* x,
         job.out_rgb = d_rgb;
         job.sobol = sc->d_sobol;
         job.exact = mode == CRAY_TRAVERSE_EXACT;
+        job.f32 = mode == CRAY_TRAVERSE_F32;
         const uint32_t capacity = (uint32_t)std::min<uint64_t>(n, 1u << 20);
         rc = run_wavefront(sc, job, capacity, sc->stream, nullptr);
         if (rc == CRAY_OK) e = cudaMemcpy(rgb, d_rgb, 3 * n * sizeof(double), cudaMemcpyDeviceToHost);
@@ -987,6 +1048,7 @@ int cray_render_device(cray_scene* sc, int mode, uint64_t seed, uint32_t sample_
         job.film = ps->d_film;
         job.sobol = sc->d_sobol;
         job.exact = mode == CRAY_TRAVERSE_EXACT;
+        job.f32 = mode == CRAY_TRAVERSE_F32;
         uint32_t pool_log2 = 23;  // path slots in flight (1.7 GB of path state); CRAY_POOL_LOG2 overrides it for tuning
         if (const char* e = std::getenv("CRAY_POOL_LOG2")) pool_log2 = (uint32_t)std::max(10, std::min(26, std::atoi(e)));
         const uint32_t capacity = (uint32_t)std::min<uint64_t>(n_total, 1ull << pool_log2);

@@ -147,6 +147,7 @@ typedef struct cray_scene cray_scene;   /* opaque; owns all device memory on its
 /* Traversal structures built at create time. */
 #define CRAY_BUILD_EXACT 1u   /* reference binary SAH BVH, f64 boxes, reference visit order (bvh.rs:58-147) */
 #define CRAY_BUILD_FAST 2u    /* 8-wide quantised BVH collapsed from the same tree */
+#define CRAY_BUILD_F32 4u     /* + 48-byte f32 triangle records beside the wide BVH (implies CRAY_BUILD_FAST) */
 
 int cray_scene_create(const cray_scene_desc* desc, int device, uint32_t build_flags, cray_scene** out);
 /* The same scene on n devices of this process (for cray_render_multi): the BVH build and the record arrays are made once
@@ -175,7 +176,12 @@ typedef struct cray_surface {      /* the rest of PrimitiveIntersection  src/int
     double uv[2];
 } cray_surface;
 
-enum { CRAY_TRAVERSE_EXACT = 0, CRAY_TRAVERSE_FAST = 1 };
+/* EXACT and FAST return the reference's primitive and distance bit for bit (FAST: up to the reference's own false box
+ * misses, which only EXACT reproduces).  F32 is the opt-in fast mode of SURVEY 8f n4: the same wide BVH, triangles tested in
+ * f32 with the watertight test of Woop, Benthin and Wald (2013) on ray-relative vertices, a ray never re-hits the triangle it
+ * leaves, and the hit that was found is re-evaluated in f64 -- so t, u, v equal the parity modes' whenever the same primitive
+ * is found, which f32 cannot guarantee for rays grazing an edge.  Spheres and disks stay in f64. */
+enum { CRAY_TRAVERSE_EXACT = 0, CRAY_TRAVERSE_FAST = 1, CRAY_TRAVERSE_F32 = 2 };
 
 /* Host buffers in, host buffers out (copies are part of the call). `surf` may be NULL. */
 int cray_trace_closest(cray_scene*, int mode, const cray_ray* rays, uint64_t n, cray_hit* hits, cray_surface* surf);
