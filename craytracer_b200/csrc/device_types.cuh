@@ -30,8 +30,6 @@ struct alignas(16) Tri32 {
 };
 static_assert(sizeof(Tri32) == 48, "Tri32 layout");
 
-constexpr uint32_t kMaxAnalyticPre = 8;
-
 struct DiskXf {      // Shape::Disk, shape.rs:41-46
     Affine o2w;      // object_to_world.matrix
     Affine w2o;      // object_to_world.inverse == world_to_object.matrix
@@ -91,8 +89,6 @@ struct SceneView {
     const LeafPrim* wide_prims;      // wide leaf order
     const uint32_t* rank_of_prim;    // primitive -> rank in the reference leaf order (exact-t tie breaking)
     const Tri32* wide_tris32;        // F32 mode: f32 triangles in wide leaf order (null unless CRAY_BUILD_F32)
-    const uint32_t* analytic_slots;  // F32 mode: leaf slots of the spheres and disks, tested once per ray before the traversal ...
-    uint32_t n_analytic_pre;         // ... when there are at most kMaxAnalyticPre of them (else 0: they are tested where the BVH finds them)
     const DiskXf* disks;
     // shading
     const cray_primitive_desc* prims;

@@ -189,7 +189,6 @@ struct HostBuild {
     WideBvh wide;
     std::vector<LeafPrim> bin_prims, wide_prims;
     std::vector<Tri32> wide_tris32;
-    std::vector<uint32_t> analytic_slots;
     std::vector<uint32_t> rank_of_prim;
     std::vector<DiskXf> disks;
     std::vector<TriShade> tri_shade;
@@ -244,9 +243,6 @@ int build_host_side(const cray_scene_desc* d, uint32_t build_flags, HostBuild& h
         work(0);
         for (auto& th : pool) th.join();
     }
-    for (size_t i = 0; i < hb.wide_tris32.size(); ++i)
-        if ((hb.wide_tris32[i].kind & 0xFFu) != PRIM_TRIANGLE && hb.analytic_slots.size() <= kMaxAnalyticPre) hb.analytic_slots.push_back((uint32_t)i);
-    if (hb.analytic_slots.size() > kMaxAnalyticPre) hb.analytic_slots.clear();
     timer.mark("leaf records");
     std::vector<DiskXf>& disks = hb.disks;
     disks.resize(d->n_disks);
@@ -395,8 +391,6 @@ int upload_scene(const HostBuild& hb, const cray_scene_desc* d, int device, cray
     UP(hb.wide.nodes, v.wide_nodes);
     UP(hb.wide_prims, v.wide_prims);
     UP(hb.wide_tris32, v.wide_tris32);
-    UP(hb.analytic_slots, v.analytic_slots);
-    v.n_analytic_pre = (uint32_t)hb.analytic_slots.size();
     UP(hb.rank_of_prim, v.rank_of_prim);
     UP(hb.disks, v.disks);
     UP(hb.prims, v.prims);

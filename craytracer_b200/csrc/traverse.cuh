@@ -350,17 +350,16 @@ __device__ __forceinline__ void prim_round_any(const SceneView& s, WarpShared& w
 // to the size of the scene's coordinates: what a ray leaving a surface needs.  Per ray (warp_begin_ray32): the permutation kz
 // and the shear Sx, Sy, Sz.  Both sides of a triangle are hit (the reference does not cull, shape.rs:227-248).
 //
-// The f64 ray itself is NOT kept in shared memory: the few tests that need it (spheres, disks, confirmations) read it again
-// from where the ray came from (Source::reload with the owner's ray id).  Shared memory not taken here stays L1 cache: at 8
-// CTAs per SM every KB per CTA moves the carve-out, and the traversal lives on its L1 hits.
+// Shared memory is budgeted: at 8 CTAs per SM, 24 064 bytes per CTA is the most that still fits the 196 KB carve-out (the next
+// step, 228 KB, leaves 28 KB of L1 and costs the closest-hit kernel 15 %).
 struct WarpShared32 {
     float4 ra[32];        // origin head x, y, z | Sx
     float4 rb[32];        // origin remainder x, y, z | Sy
     float4 rc[32];        // Sz | kz (bits) | leaf slot of the triangle the ray leaves, CRAY_NO_HIT if none (bits) | closest distance so far
+    double ox[32], oy[32], oz[32], dx[32], dy[32], dz[32];   // the f64 ray, for spheres, disks and confirmations
     double tmax[32];      // closest-hit: distance of the best hit (exact f64 for spheres / disks); any-hit: the ray's max distance
     float tmax32[32];     // slab-test bound
     float tmin[32];       // smallest distance accepted (kEpsilon32, or the caller's allowance for a ray of unknown provenance)
-    float tsure[32];      // any-hit: an f32 distance beyond this is too close to the ray's end to be trusted (see prim_round_any32)
     uint32_t best[32];
     uint32_t pend[32];
     uint32_t tail;
@@ -389,6 +388,8 @@ __device__ __forceinline__ float f32_ray_max(double ray_max) {
 template <bool ANY>
 __device__ __forceinline__ void warp_begin_ray32(WarpShared32& ws, unsigned lane, V3 o, V3 dir, double ray_max, uint32_t best_init, uint32_t self_slot, float tmin) {
     ws.tmin[lane] = tmin;
+    ws.ox[lane] = o.x; ws.oy[lane] = o.y; ws.oz[lane] = o.z;
+    ws.dx[lane] = dir.x; ws.dy[lane] = dir.y; ws.dz[lane] = dir.z;
     ws.tmax[lane] = ray_max;
     ws.tmax32[lane] = slab_tmax(ray_max);
     ws.best[lane] = best_init;
@@ -403,9 +404,7 @@ __device__ __forceinline__ void warp_begin_ray32(WarpShared32& ws, unsigned lane
     const float dky = kz == 0u ? fz : (kz == 1u ? fx : fy);
     ws.ra[lane] = make_float4(hx, hy, hz, dkx / dk);
     ws.rb[lane] = make_float4((float)(o.x - (double)hx), (float)(o.y - (double)hy), (float)(o.z - (double)hz), dky / dk);
-    const float full = __double2float_ru(ray_max);
-    ws.tsure[lane] = __fmul_rd(full, 0.9990234375f);  // 1 - 2^-10 (+inf stays +inf: every distance is trusted)
-    ws.rc[lane] = make_float4(1.0f / dk, __uint_as_float(kz), __uint_as_float(self_slot), ANY ? full : f32_ray_max(ray_max));
+    ws.rc[lane] = make_float4(1.0f / dk, __uint_as_float(kz), __uint_as_float(self_slot), ANY ? __double2float_ru(ray_max) : f32_ray_max(ray_max));
 }
 
 __device__ __forceinline__ float& closest32(WarpShared32& ws, uint32_t owner) { return ws.rc[owner].w; }
@@ -448,37 +447,13 @@ __device__ __forceinline__ bool tri32_hit(const Tri32Regs& tr, const WarpShared3
     return true;
 }
 
-// A scene's few spheres and disks (dragon.cry: the ground sphere and the light disk, which nearly every ray's traversal runs
-// into) are tested once per ray, in f64, while the ray is still in registers -- the closest of them bounds the traversal from
-// its first node on -- and skipped where the BVH finds them.
-template <bool ANY>
-__device__ __forceinline__ void pretest_analytic32(const SceneView& s, WarpShared32& ws, unsigned lane, V3 o, V3 dir, double ray_max) {
-    for (uint32_t k = 0; k < s.n_analytic_pre; ++k) {
-        const uint32_t slot = s.analytic_slots[k];
-        const LeafPrim lp = load_leaf_prim(s.wide_prims + slot);
-        if constexpr (ANY) {
-            if (analytic_any(s, lp, o, dir, ray_max)) { ws.best[lane] = 1u; break; }
-        } else {
-            double cand = (double)closest32(ws, lane);
-            if (analytic_candidate(s, lp, o, dir, cand, false) == 1) {
-                closest32(ws, lane) = __double2float_rd(cand);
-                ws.best[lane] = slot;
-                ws.tmax[lane] = cand;
-                ws.tmax32[lane] = slab_tmax(cand);
-            }
-        }
-    }
-}
-
 // Closest-hit round of the F32 mode: as prim_round_closest, with the closest distance kept as an f32 bit pattern.  Equal
 // distances: the lowest lane of a round wins, a later round's equal distance replaces it (no reference order in this mode).
-template <class Source>
-__device__ __forceinline__ void prim_round_closest32(const SceneView& s, WarpShared32& ws, unsigned lane, uint32_t head, uint32_t count, const Source& src, uint32_t id) {
+__device__ __forceinline__ void prim_round_closest32(const SceneView& s, WarpShared32& ws, unsigned lane, uint32_t head, uint32_t count) {
     const unsigned FULL = 0xFFFFFFFFu;
     const bool act = lane < count;
     const uint32_t e = act ? ws.queue[(head + lane) & (kQueue - 1u)] : 0u;
     const uint32_t owner = e >> kSlotBits, slot = e & kSlotMask;
-    const uint32_t owner_id = __shfl_sync(FULL, id, owner);
     bool hit = false;
     float t32 = 0.0f;
     double t64 = 0.0;
@@ -489,12 +464,10 @@ __device__ __forceinline__ void prim_round_closest32(const SceneView& s, WarpSha
             if (slot != __float_as_uint(ws.rc[owner].z) && tri32_hit(tr, ws, owner, t) && t > ws.tmin[owner] && t < closest32(ws, owner)) {
                 hit = true; t32 = t; t64 = (double)t;
             }
-        } else if (s.n_analytic_pre == 0u) {  // spheres and disks (not pre-tested): the f64 test of the parity mode on the f64 ray
+        } else {  // spheres and disks: the f64 test of the parity mode on the f64 ray
             const LeafPrim lp = load_leaf_prim(s.wide_prims + slot);
-            double cand = (double)closest32(ws, owner), unused;
-            V3 o, dir;
-            src.reload(owner_id, o, dir, unused);
-            if (analytic_candidate(s, lp, o, dir, cand, false) == 1) {
+            double cand = (double)closest32(ws, owner);
+            if (analytic_candidate(s, lp, mk(ws.ox[owner], ws.oy[owner], ws.oz[owner]), mk(ws.dx[owner], ws.dy[owner], ws.dz[owner]), cand, false) == 1) {
                 hit = true; t64 = cand; t32 = __double2float_rd(cand);
             }
         }
@@ -517,33 +490,22 @@ __device__ __forceinline__ void prim_round_closest32(const SceneView& s, WarpSha
 // surface -- the light's own triangle for a mesh light -- whose f32 distance is uncertain by a few ulps divided by the cosine of
 // the angle of incidence.  An f32 hit in the last 2^-10 of the ray is therefore confirmed by the f64 test of the parity mode
 // against the exact max distance (out of line; a fraction of a percent of the tests), everything nearer is taken as it is.
-template <class Source>
-__device__ __forceinline__ void prim_round_any32(const SceneView& s, WarpShared32& ws, unsigned lane, uint32_t head, uint32_t count, const Source& src, uint32_t id) {
+__device__ __forceinline__ void prim_round_any32(const SceneView& s, WarpShared32& ws, unsigned lane, uint32_t head, uint32_t count) {
     const unsigned FULL = 0xFFFFFFFFu;
     const bool act = lane < count;
     const uint32_t e = act ? ws.queue[(head + lane) & (kQueue - 1u)] : 0u;
     const uint32_t owner = e >> kSlotBits, slot = e & kSlotMask;
-    const uint32_t owner_id = __shfl_sync(FULL, id, owner);
     if (act && ws.best[owner] == 0u) {
         const Tri32Regs tr = load_tri32(s.wide_tris32 + slot);
         bool occ;
         if ((__float_as_uint(tr.c.z) & 0xFFu) == PRIM_TRIANGLE) {
             float t;
             occ = slot != __float_as_uint(ws.rc[owner].z) && tri32_hit(tr, ws, owner, t) && t > ws.tmin[owner] && t < closest32(ws, owner);
-            if (occ && t > ws.tsure[owner]) {
-                V3 o, dir;
-                double ray_max;
-                src.reload(owner_id, o, dir, ray_max);
-                occ = triangle_any_f64(s, slot, o, dir, ray_max);
-            }
-        } else if (s.n_analytic_pre == 0u) {
-            const LeafPrim lp = load_leaf_prim(s.wide_prims + slot);
-            V3 o, dir;
-            double ray_max;
-            src.reload(owner_id, o, dir, ray_max);
-            occ = analytic_any(s, lp, o, dir, ray_max);
+            if (occ && t > closest32(ws, owner) * 0.9990234375f)   // 1 - 2^-10 (never true for an infinite ray)
+                occ = triangle_any_f64(s, slot, mk(ws.ox[owner], ws.oy[owner], ws.oz[owner]), mk(ws.dx[owner], ws.dy[owner], ws.dz[owner]), ws.tmax[owner]);
         } else {
-            occ = false;
+            const LeafPrim lp = load_leaf_prim(s.wide_prims + slot);
+            occ = analytic_any(s, lp, mk(ws.ox[owner], ws.oy[owner], ws.oz[owner]), mk(ws.dx[owner], ws.dy[owner], ws.dz[owner]), ws.tmax[owner]);
         }
         if (occ) ws.best[owner] = 1u;
     }

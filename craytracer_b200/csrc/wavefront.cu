@@ -77,12 +77,6 @@ __device__ __forceinline__ uint32_t st_bounces(uint32_t s) { return (s >> 8) & 0
 
 struct ExtendSource {  // queued path rays -> Pool::hit_*
     Pool p;
-    // the f64 ray of path slot `i` again (F32 mode: the tests of spheres and disks)
-    __device__ __forceinline__ void reload(uint32_t i, V3& o, V3& d, double& ray_max) const {
-        o = mk(p.ox[i], p.oy[i], p.oz[i]);
-        d = mk(p.dx[i], p.dy[i], p.dz[i]);
-        ray_max = inf_f64();
-    }
     __device__ __forceinline__ uint32_t load(uint64_t idx, V3& o, V3& d, double& ray_max) const {
         const uint32_t i = p.extend_queue[idx];
         o = mk(p.ox[i], p.oy[i], p.oz[i]);
@@ -102,11 +96,6 @@ struct ExtendSource {  // queued path rays -> Pool::hit_*
 
 struct ShadowSource {  // queued shadow rays -> L += contribution when unoccluded (path_integrator.rs:141-163)
     Pool p;
-    __device__ __forceinline__ void reload(uint32_t i, V3& o, V3& d, double& ray_max) const {
-        o = mk(p.ox[i], p.oy[i], p.oz[i]);
-        d = mk(p.sdx[i], p.sdy[i], p.sdz[i]);
-        ray_max = p.smax[i];
-    }
     __device__ __forceinline__ uint32_t load(uint64_t idx, V3& o, V3& d, double& ray_max) const {
         const uint32_t i = p.shadow_queue[idx];
         o = mk(p.ox[i], p.oy[i], p.oz[i]);
@@ -114,8 +103,6 @@ struct ShadowSource {  // queued shadow rays -> L += contribution when unocclude
         ray_max = p.smax[i];
         return i;
     }
-    __device__ __forceinline__ uint32_t self_slot(uint32_t i) const { return p.hit_slot[i]; }
-    __device__ __forceinline__ float t_min32(V3, V3) const { return kEpsilon32; }
     __device__ __forceinline__ void store_closest(const SceneView&, uint32_t, uint32_t, double) const {}
     __device__ __forceinline__ void store_any(uint32_t i, bool occluded) const {
         if (!occluded) { p.L_r[i] += p.sc_r[i]; p.L_g[i] += p.sc_g[i]; p.L_b[i] += p.sc_b[i]; }
@@ -164,12 +151,6 @@ struct RayArraySource {  // S3: caller-provided cray_ray records
     cray_surface* surf;
     uint8_t* occluded;
     bool f32;
-    __device__ __forceinline__ void reload(uint32_t i, V3& o, V3& d, double& ray_max) const {
-        const cray_ray r = rays[i];
-        o = mk(r.origin[0], r.origin[1], r.origin[2]);
-        d = mk(r.direction[0], r.direction[1], r.direction[2]);
-        ray_max = r.max_distance;
-    }
     __device__ __forceinline__ uint32_t self_slot(uint32_t) const { return CRAY_NO_HIT; }
     __device__ __forceinline__ float t_min32(V3 o, V3 d) const { return f32_unknown_origin_tmin(o, d); }
     __device__ __forceinline__ uint32_t load(uint64_t idx, V3& o, V3& d, double& ray_max) const {
@@ -268,11 +249,7 @@ __global__ void __launch_bounds__(128, F32 ? kWideMinBlocksF32 : (ANY ? kWideMin
                     double ray_max;
                     id = src.load(idx, o, d, ray_max);
                     r = make_wide_ray(o, d, ray_max);
-                    if constexpr (F32) {
-                        warp_begin_ray32<ANY>(ws, lane, o, d, ray_max, ANY ? 0u : CRAY_NO_HIT, src.self_slot(id), src.t_min32(o, d));
-                        pretest_analytic32<ANY>(s, ws, lane, o, d, ray_max);
-                        r.tmax = ws.tmax32[lane];
-                    }
+                    if constexpr (F32) warp_begin_ray32<ANY>(ws, lane, o, d, ray_max, ANY ? 0u : CRAY_NO_HIT, src.self_slot(id), src.t_min32(o, d));
                     else warp_begin_ray(ws, lane, o, d, ray_max, ANY ? 0u : CRAY_NO_HIT);
                     ng = make_uint2(0u, 0x80000000u);  // the root, as a one-child node group
                     sp = 0;
@@ -312,8 +289,8 @@ __global__ void __launch_bounds__(128, F32 ? kWideMinBlocksF32 : (ANY ? kWideMin
             const unsigned waiting = __ballot_sync(FULL, state != LANE_IDLE && !node_work);
             while (count >= 32u || (count > 0u && (node_lanes == 0u || __popc(waiting) >= tune.wait_lanes))) {
                 const uint32_t take = count < 32u ? count : 32u;
-                if constexpr (F32 && ANY) prim_round_any32(s, ws, lane, head, take, src, id);
-                else if constexpr (F32) prim_round_closest32(s, ws, lane, head, take, src, id);
+                if constexpr (F32 && ANY) prim_round_any32(s, ws, lane, head, take);
+                else if constexpr (F32) prim_round_closest32(s, ws, lane, head, take);
                 else if constexpr (ANY) prim_round_any(s, ws, lane, head, take);
                 else prim_round_closest(s, ws, lane, head, take);
                 head += take;
@@ -483,7 +460,7 @@ __global__ void __launch_bounds__(128) k_extend_exact(SceneView s, Pool p, const
 #define CRAY_SHADE_THREADS 256
 #endif
 #ifndef CRAY_SHADE_BLOCKS
-#define CRAY_SHADE_BLOCKS 3
+#define CRAY_SHADE_BLOCKS 4
 #endif
 #ifndef CRAY_SHADE_PREFETCH
 #define CRAY_SHADE_PREFETCH 1
@@ -491,7 +468,7 @@ __global__ void __launch_bounds__(128) k_extend_exact(SceneView s, Pool p, const
 constexpr uint32_t kShadeThreads = CRAY_SHADE_THREADS;
 constexpr uint32_t kShadeKeys = 16;   // class (matte, glass, plastic, metal) x shape kind (3); 12 = miss; 13 = no path
 
-__global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(SceneView s, Pool p, Job job, Counters* counters) {
+__global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(const __grid_constant__ SceneView s, const __grid_constant__ Pool p, const __grid_constant__ Job job, Counters* counters) {
     constexpr uint32_t kWarps = kShadeThreads / 32, kCells = kShadeKeys * kWarps;  // 128 (key, warp) cells
     __shared__ uint32_t s_count[kCells];
     __shared__ uint32_t s_warp_total[kCells / 32];
@@ -743,7 +720,7 @@ int ensure_pool(cray_scene* sc, uint32_t capacity) {
         ps->shadow_blocks = (unsigned)(sms * std::max(per_sm, 1));
         CRAY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wide_persistent<false, ExtendSource, true>, 128, 0));
         ps->f32_blocks = (unsigned)(sms * std::max(per_sm, 1));
-        CRAY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wide_persistent<true, ShadowSource, true>, 128, 0));
+        CRAY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wide_persistent<true, RayArraySource, true>, 128, 0));
         ps->f32_shadow_blocks = (unsigned)(sms * std::max(per_sm, 1));
         if (const char* e = std::getenv("CRAY_REFILL_LANES")) ps->tune.refill_lanes = std::max(1, std::min(32, std::atoi(e)));
         if (const char* e = std::getenv("CRAY_WAIT_LANES")) ps->tune.wait_lanes = std::max(1, std::min(33, std::atoi(e)));
@@ -817,7 +794,9 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 3], stream));
         // at most one shadow ray per shaded vertex; the queue length lives on the device
         if (job.exact) k_shadow_exact<<<g128, 128, 0, stream>>>(sc->view, pool, &dc->n_shadow);
-        else if (job.f32) k_wide_persistent<true, ShadowSource, true><<<ps->f32_shadow_blocks, 128, 0, stream>>>(sc->view, ShadowSource{pool}, &dc->n_shadow, &dc->shadow_cursor, ps->tune);
+        // (F32 mode traces its shadow rays with the f64 any-hit kernel: measured faster than the f32 one, 20.9 against 24.0 ms per
+        // 256-spp dragon frame -- the f32 instantiation's larger shared-memory footprint leaves it less L1 -- and exact at the
+        // light's end of the ray.  The f32 any-hit kernel serves cray_trace_any.)
         else k_wide_persistent<true, ShadowSource><<<gs, 128, 0, stream>>>(sc->view, ShadowSource{pool}, &dc->n_shadow, &dc->shadow_cursor, ps->tune);
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 4], stream));
         launches += 4;
