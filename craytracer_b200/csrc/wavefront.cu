@@ -380,10 +380,36 @@ __device__ __forceinline__ void camera_ray(const DevCamera& c, double fu, double
     d = xf_vector(c.world_from_camera, rd);
 }
 
-__global__ void __launch_bounds__(256) k_generate(SceneView s, Pool p, Job job, Counters* counters) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.capacity) return;
-    uint32_t st = p.state[i];
+// Block-wide exclusive rank of the threads with `pred` (ascending thread order) and their total.  `s_warp` = 8 words of shared
+// memory; ends with a barrier, so it can be called again right away.
+__device__ __forceinline__ uint32_t block_rank_256(bool pred, uint32_t* s_warp, uint32_t& total) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (unsigned w = 0; w < 8; ++w) {
+        const uint32_t c = s_warp[w];
+        before += w < warp ? c : 0u;
+        all += c;
+    }
+    __syncthreads();
+    total = all;
+    return before + __popc(m & ((1u << lane) - 1u));
+}
+
+// One block = 256 consecutive path slots.  Finished paths are flushed by their own thread; the slots to refill are then
+// compacted, so that the camera-ray code (SipHash, four Sobol values, f64 camera transform) runs on full warps instead of on the
+// scattered third of the lanes whose path happened to end -- and the sample ids and the extend-queue range of the whole block
+// are each claimed with ONE atomic.
+__global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneView s, const __grid_constant__ Pool p, const __grid_constant__ Job job, Counters* counters) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_list[256];
+    __shared__ unsigned long long s_base[2];
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    const bool in_range = i < p.capacity;
+    uint32_t st = in_range ? p.state[i] : 0xFFu;  // 0xFF: no slot
     if (st_state(st) == SLOT_DONE) {
         // flush: craytracer.rs:177-188 accumulates the sample into its pixel; a sample on which the reference would
         // have panicked (path_integrator.rs:208-209 and the asserts of its callees) is dropped and counted
@@ -400,17 +426,20 @@ __global__ void __launch_bounds__(256) k_generate(SceneView s, Pool p, Job job, 
             dst[0] = r; dst[1] = g; dst[2] = b;
         }
         st = SLOT_EMPTY;
+        p.state[i] = st;
     }
-    if (st_state(st) == SLOT_EMPTY) {
-        // claim the next sample id (warp-aggregated)
-        const unsigned mask = __activemask();
-        const unsigned lane = threadIdx.x & 31;
-        const unsigned leader = __ffs(mask) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(&counters->next_id, (unsigned long long)__popc(mask));
-        base = __shfl_sync(mask, base, leader);
-        const unsigned long long id = base + __popc(mask & ((1u << lane) - 1u));
+    // the empty slots of this block, compacted
+    const bool empty = st_state(st) == SLOT_EMPTY;
+    uint32_t n_empty;
+    const uint32_t rank = block_rank_256(empty, s_warp, n_empty);
+    if (empty) s_list[rank] = i;
+    if (threadIdx.x == 0 && n_empty) s_base[0] = atomicAdd(&counters->next_id, (unsigned long long)n_empty);
+    __syncthreads();
+    const unsigned long long id_base = n_empty ? s_base[0] : 0ull;
+    if (threadIdx.x < n_empty) {
+        const unsigned long long id = id_base + threadIdx.x;
         if (id < job.n_total) {
+            const uint32_t slot = s_list[threadIdx.x];
             uint32_t x, y, si;
             if (job.lx) { x = job.lx[id]; y = job.ly[id]; si = job.ls[id]; }
             else {
@@ -424,22 +453,26 @@ __global__ void __launch_bounds__(256) k_generate(SceneView s, Pool p, Job job, 
             const double lu = smp.sample_1d(job.sobol), lv = smp.sample_1d(job.sobol);
             V3 o, d;
             camera_ray(s.camera, fu, fv, lu, lv, x, y, o, d);
-            p.ox[i] = o.x; p.oy[i] = o.y; p.oz[i] = o.z;
-            p.dx[i] = d.x; p.dy[i] = d.y; p.dz[i] = d.z;
-            p.beta_r[i] = 1.0; p.beta_g[i] = 1.0; p.beta_b[i] = 1.0;
-            p.L_r[i] = 0.0; p.L_g[i] = 0.0; p.L_b[i] = 0.0;
-            p.prev_bsdf_pdf[i] = 0.0;
-            p.hit_slot[i] = CRAY_NO_HIT;  // a camera ray leaves no surface (F32 mode's self-intersection rule)
-            p.id[i] = (uint32_t)id;
-            p.pixel[i] = x + y * s.camera.width;
-            p.hash[i] = smp.hash;
-            p.shuffled_rev[i] = smp.shuffled_rev;
-            st = SLOT_ACTIVE | (1u << 16);  // bounces = 0, is_specular_bounce = true (path_integrator.rs:50)
+            p.ox[slot] = o.x; p.oy[slot] = o.y; p.oz[slot] = o.z;
+            p.dx[slot] = d.x; p.dy[slot] = d.y; p.dz[slot] = d.z;
+            p.beta_r[slot] = 1.0; p.beta_g[slot] = 1.0; p.beta_b[slot] = 1.0;
+            p.L_r[slot] = 0.0; p.L_g[slot] = 0.0; p.L_b[slot] = 0.0;
+            p.prev_bsdf_pdf[slot] = 0.0;
+            p.hit_slot[slot] = CRAY_NO_HIT;  // a camera ray leaves no surface (F32 mode's self-intersection rule)
+            p.id[slot] = (uint32_t)id;
+            p.pixel[slot] = x + y * s.camera.width;
+            p.hash[slot] = smp.hash;
+            p.shuffled_rev[slot] = smp.shuffled_rev;
+            p.state[slot] = SLOT_ACTIVE | (1u << 16);  // bounces = 0, is_specular_bounce = true (path_integrator.rs:50)
         }
     }
-    p.state[i] = st;
-    // every live slot has a ray to extend this iteration
-    if (st_state(st) == SLOT_ACTIVE) queue_append(&counters->n_extend, p.extend_queue, i);
+    // every live slot has a ray to extend this iteration: the block's slots go to the queue in ascending order
+    const bool live = st_state(st) == SLOT_ACTIVE || (empty && id_base + rank < job.n_total);
+    uint32_t n_live;
+    const uint32_t qrank = block_rank_256(live, s_warp, n_live);
+    if (threadIdx.x == 0 && n_live) s_base[1] = atomicAdd(&counters->n_extend, (unsigned long long)n_live);
+    __syncthreads();
+    if (live) p.extend_queue[s_base[1] + qrank] = i;
 }
 
 __global__ void __launch_bounds__(128) k_extend_exact(SceneView s, Pool p, const unsigned long long* __restrict__ n_ptr) {
