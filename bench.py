@@ -24,6 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALGORITHMIC_BYTES_PER_RAY = 904  # 32 ray + 16 hit + 8 levels x 80 B wide node + 3 x 72 B f64 triangles
+ALGORITHMIC_BYTES_PER_RAY_F32 = 796  # the same with 3 x 36 B f32 triangles (the records as stored are 48 B)
 WORKLOAD = "dragon.cry 600x400 (7 219 045-triangle procedural stand-in for xyzrgb_dragon.obj)"
 
 
@@ -219,7 +220,8 @@ def run_ours(args):
 
     hs, parse_s = build_host_scene(args)
     t0 = time.time()
-    scene = c.Scene(hs, device=local_rank, build=c.BUILD_EXACT | c.BUILD_FAST | (c.BUILD_F32 if args.mode == "f32" else 0))
+    also_f32 = world == 1 and args.mode == "fast" and not args.no_f32_leg
+    scene = c.Scene(hs, device=local_rank, build=c.BUILD_EXACT | c.BUILD_FAST | (c.BUILD_F32 if args.mode == "f32" or also_f32 else 0))
     create_s = time.time() - t0
     mode = {"exact": c.TRAVERSE_EXACT, "fast": c.TRAVERSE_FAST, "f32": c.TRAVERSE_F32}[args.mode]
     lo, hi = shard_samples(args.spp, rank, world)
@@ -231,7 +233,7 @@ def run_ours(args):
     host_np = host_film.numpy()
     job_bytes = 8 + 4 + 4  # the per-step host->device input of a render call: seed, sample_begin, sample_end (the scene is resident)
 
-    def step(seed, e2e):
+    def step(seed, e2e, mode=mode):
         if e2e and world == 1:
             # the reference-facing call with a HOST film buffer: cray_render (include/cray_b200.h, replaces render()
             # src/bin/craytracer.rs:224); device->host copy of the film inside the call
@@ -247,7 +249,7 @@ def run_ours(args):
                 host_film.copy_(film, non_blocking=True)  # the film the reference hands to on_render_finish
         return st
 
-    def timed(e2e):
+    def timed(e2e, mode=mode):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -257,7 +259,7 @@ def run_ours(args):
         start.record(stream)
         for k in range(args.steps):
             t_host = time.perf_counter()
-            st = step(k, e2e)
+            st = step(k, e2e, mode)
             totals["host_ms"] = totals.get("host_ms", 0.0) + (time.perf_counter() - t_host) * 1e3
             totals["closest"] += st.closest_rays
             totals["shadow"] += st.shadow_rays
@@ -291,6 +293,17 @@ def run_ours(args):
     ms_dev, counts_dev, totals = timed(False)
     ms_e2e, counts_e2e, _ = timed(True)
     clocks = sampler.stop() if sampler else None
+    f32_leg = None
+    if also_f32:  # the opt-in F32 traversal mode beside the headline (parity) mode: same frame, same timing rules
+        step(3000, False, c.TRAVERSE_F32)
+        ms32, counts32, totals32 = timed(False, c.TRAVERSE_F32)
+        f32_leg = {"value": (counts32[0] + counts32[1]) / ms32 / 1e3, "unit": "Mrays/s", "ms_per_step": ms32 / args.steps,
+                   "stage_ms_per_step": {"extend": totals32["trace_ms"] / args.steps, "shade": totals32["shade_ms"] / args.steps,
+                                         "shadow": totals32["shadow_ms"] / args.steps, "generate": totals32["generate_ms"] / args.steps},
+                   "extend_achieved_gbs": totals32["closest"] * ALGORITHMIC_BYTES_PER_RAY_F32 / (totals32["trace_ms"] * 1e-3) / 1e9,
+                   "algorithmic_bytes_per_ray": ALGORITHMIC_BYTES_PER_RAY_F32,
+                   "note": "CRAY_TRAVERSE_F32 (SURVEY 8f n4), opt-in: f32 watertight triangle tests on the same wide BVH, hits re-evaluated in f64; "
+                           "not the headline because a ray grazing an edge may find the neighbouring triangle (tests/test_gpu_f32_mode.py)"}
 
     if rank == 0:
         rays = counts_dev[0] + counts_dev[1]
@@ -299,8 +312,9 @@ def run_ours(args):
         peak, peak_kind = measured_peaks()
         # dominant kernel: k_wide_persistent<false> (closest-hit traversal); CUDA-event time of its launches on rank 0 inside the timed region
         extend_ms = totals["trace_ms"]
-        achieved = totals["closest"] * ALGORITHMIC_BYTES_PER_RAY / (extend_ms * 1e-3) / 1e9 if extend_ms > 0 else 0.0
-        traffic = profiled_traffic()
+        bytes_per_ray = ALGORITHMIC_BYTES_PER_RAY_F32 if args.mode == "f32" else ALGORITHMIC_BYTES_PER_RAY
+        achieved = totals["closest"] * bytes_per_ray / (extend_ms * 1e-3) / 1e9 if extend_ms > 0 else 0.0
+        traffic = profiled_traffic() if args.mode == "fast" else None
         line = {
             "metric": "Mrays/s on dragon.cry", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -314,8 +328,8 @@ def run_ours(args):
                             "the scene is resident like the reference's &Scene, so the per-step host->device input is the job description only; "
                             "scene upload is reported under setup.upload_ms"},
             "gpu_launches": int(counts_dev[2]),
-            "roofline": {"bound": "hbm", "kernel": "k_wide_persistent<false, ExtendSource> (closest-hit traversal, 8-wide BVH)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_kind, "algorithmic_bytes_per_ray": ALGORITHMIC_BYTES_PER_RAY,
+            "roofline": {"bound": "hbm", "kernel": "k_wide_persistent<false, ExtendSource" + (", true" if args.mode == "f32" else "") + "> (closest-hit traversal, 8-wide BVH)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_kind, "algorithmic_bytes_per_ray": bytes_per_ray,
                          "rays_in_kernel": totals["closest"], "kernel_ms": extend_ms, "kernel_share_of_step": extend_ms / max(totals["render_ms"], 1e-9),
                          "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "traffic_detail": traffic},
             "stage_ms_per_step": {"extend": totals["trace_ms"] / args.steps, "shade": totals["shade_ms"] / args.steps, "shadow": totals["shadow_ms"] / args.steps,
@@ -326,6 +340,8 @@ def run_ours(args):
                       "wide_nodes": scene.info.wide_nodes, "wide_depth": scene.info.wide_depth, "triangles": hs.desc.n_triangles},
             "dropped_samples": totals["nan"],
         }
+        if f32_leg:
+            line["f32_mode"] = f32_leg
         if world == 1 and not args.no_cpu_baseline:
             scene.close()
             _, base = cpu_baseline(hs, args, budget_s=args.cpu_budget)
@@ -343,6 +359,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-f32-leg", action="store_true", help="skip the extra timed leg in the opt-in F32 traversal mode (N=1, --mode fast)")
     ap.add_argument("--spp", type=int, default=1024)
     ap.add_argument("--width", type=int, default=600)
     ap.add_argument("--height", type=int, default=400)

@@ -2,7 +2,7 @@
 # sweep of library variants (make VARIANT=...) on the GPU box:  VARIANTS="_a _b" SPP=256 bash tools/sweep.sh
 run() {  # label, env...
   label=$1; shift
-  env "$@" python bench.py --spp ${SPP:-256} --steps 2 --warmup 2 --no-cpu-baseline 2>/dev/null | python -c "
+  env "$@" python bench.py --spp ${SPP:-256} --steps 2 --warmup 2 --no-cpu-baseline --no-f32-leg 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 st=d['stage_ms_per_step']
