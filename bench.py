@@ -28,6 +28,28 @@ ALGORITHMIC_BYTES_PER_RAY_F32 = 796  # the same with 3 x 36 B f32 triangles (SUR
 WORKLOAD = "dragon.cry 600x400 (7 219 045-triangle procedural stand-in for xyzrgb_dragon.obj)"
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on init), so the
+    process's fd 1 is pointed at stderr for the whole run and the result line goes to a private copy of the original stdout."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -198,7 +220,7 @@ def run_reference(args):
             "samples_per_s": args.width * args.height * spp * args.steps / dt,
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -346,7 +368,7 @@ def run_ours(args):
             scene.close()
             _, base = cpu_baseline(hs, args, budget_s=args.cpu_budget)
             line["cpu_baseline"] = base
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -369,6 +391,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of host work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
