@@ -738,6 +738,24 @@ struct PoolStorage {
     std::vector<cudaEvent_t> timers;                 // stage boundaries of every iteration of one render, reused across calls
 };
 
+// Resident CTAs per SM of a persistent traversal kernel -- and the shared-memory carve-out asked for is exactly what those
+// CTAs need, so that the rest of the 256 KB stays L1.  Left to itself the driver sizes the carve-out for the occupancy shared
+// memory alone would allow (closest-hit kernel: 132 KB for 7 CTAs where registers admit 5 -- 35 KB of L1 given away).
+// CRAY_CARVEOUT=0 keeps the driver's choice (tuning).
+template <class Kernel>
+int resident_blocks(Kernel kernel, int* per_sm) {
+    CRAY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kernel, 128, 0));
+    *per_sm = std::max(*per_sm, 1);
+    const char* e = std::getenv("CRAY_CARVEOUT");
+    if (e && std::atoi(e) == 0) return CRAY_OK;
+    cudaFuncAttributes attr{};
+    CRAY_CUDA(cudaFuncGetAttributes(&attr, kernel));
+    const size_t need = (size_t)*per_sm * (attr.sharedSizeBytes + 1024);  // + the 1 KB the system reserves per CTA
+    const int percent = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024));
+    CRAY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, percent));
+    return CRAY_OK;
+}
+
 int ensure_pool(cray_scene* sc, uint32_t capacity) {
     auto* ps = static_cast<PoolStorage*>(sc->pool);
     if (!ps) { ps = new PoolStorage(); sc->pool = ps; }
@@ -747,14 +765,20 @@ int ensure_pool(cray_scene* sc, uint32_t capacity) {
         int sms = 0;
         CRAY_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sc->device));
         int per_sm = 0;
-        CRAY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wide_persistent<false, ExtendSource>, 128, 0));
-        ps->persistent_blocks = (unsigned)(sms * std::max(per_sm, 1));
-        CRAY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wide_persistent<true, ShadowSource>, 128, 0));
-        ps->shadow_blocks = (unsigned)(sms * std::max(per_sm, 1));
-        CRAY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wide_persistent<false, ExtendSource, true>, 128, 0));
-        ps->f32_blocks = (unsigned)(sms * std::max(per_sm, 1));
-        CRAY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wide_persistent<true, RayArraySource, true>, 128, 0));
-        ps->f32_shadow_blocks = (unsigned)(sms * std::max(per_sm, 1));
+        int rc = resident_blocks(k_wide_persistent<false, ExtendSource>, &per_sm);
+        if (rc != CRAY_OK) return rc;
+        ps->persistent_blocks = (unsigned)(sms * per_sm);
+        if ((rc = resident_blocks(k_wide_persistent<true, ShadowSource>, &per_sm)) != CRAY_OK) return rc;
+        ps->shadow_blocks = (unsigned)(sms * per_sm);
+        if ((rc = resident_blocks(k_wide_persistent<false, ExtendSource, true>, &per_sm)) != CRAY_OK) return rc;
+        ps->f32_blocks = (unsigned)(sms * per_sm);
+        if ((rc = resident_blocks(k_wide_persistent<true, RayArraySource, true>, &per_sm)) != CRAY_OK) return rc;
+        ps->f32_shadow_blocks = (unsigned)(sms * per_sm);
+        // the S3 instantiations share the budgets of their wavefront twins
+        int unused = 0;
+        if ((rc = resident_blocks(k_wide_persistent<false, RayArraySource>, &unused)) != CRAY_OK) return rc;
+        if ((rc = resident_blocks(k_wide_persistent<true, RayArraySource>, &unused)) != CRAY_OK) return rc;
+        if ((rc = resident_blocks(k_wide_persistent<false, RayArraySource, true>, &unused)) != CRAY_OK) return rc;
         if (const char* e = std::getenv("CRAY_REFILL_LANES")) ps->tune.refill_lanes = std::max(1, std::min(32, std::atoi(e)));
         if (const char* e = std::getenv("CRAY_WAIT_LANES")) ps->tune.wait_lanes = std::max(1, std::min(33, std::atoi(e)));
         if (const char* e = std::getenv("CRAY_BLOCKS_PER_SM")) ps->persistent_blocks = ps->shadow_blocks = ps->f32_blocks = ps->f32_shadow_blocks = (unsigned)(sms * std::max(1, std::atoi(e)));
