@@ -164,3 +164,48 @@ def test_f32_mode_needs_its_build_flag():
     assert "CRAY_BUILD_F32" in str(info.value)
     with pytest.raises(c.CrayError):
         gpu.render(seed=0, sample_begin=0, sample_end=1, mode=c.TRAVERSE_F32)
+
+
+def test_f32_edge_case_rays():
+    """Empty batches, axis-aligned rays (zero direction components), tiny / finite max distances, a zero direction and
+    non-finite components: no fault, every answer is a valid primitive or a miss, and away from the deliberately grazing rays
+    the answers are the parity mode's."""
+    hs, gpu, orc = get_scene("test")
+    assert len(gpu.intersect(np.empty(0, dtype=c.RAY_DTYPE), mode=c.TRAVERSE_F32)) == 0
+    assert len(gpu.intersects(np.empty(0, dtype=c.RAY_DTYPE), mode=c.TRAVERSE_F32)) == 0
+    o_, d_, m_ = [], [], []
+    for axis in range(3):
+        for sign in (1.0, -1.0):
+            for org in ([0.26, 0.27, -3.0], [2.5, 2.0, 3.0], [1.5, 5.0, -1.0], [0.01, 0.02, 0.03], [0.5, 0.25, -1.0]):
+                d = [0.0, 0.0, 0.0]
+                d[axis] = sign
+                o_.append(org); d_.append(d); m_.append(np.inf)
+    for tmax in (1e-12, 1e-9, 2e-9, 0.5, 2.9, 3.1):
+        o_.append([0.26, 0.27, -3.0]); d_.append([0.0, 0.0, 1.0]); m_.append(tmax)
+    n_regular = len(o_)
+    o_.append([0.0, 0.0, 0.0]); d_.append([0.0, 0.0, 0.0]); m_.append(np.inf)             # no direction at all
+    o_.append([np.nan, 0.0, 0.0]); d_.append([0.0, 0.0, 1.0]); m_.append(np.inf)
+    o_.append([0.0, 0.0, 0.0]); d_.append([np.inf, 0.0, 1.0]); m_.append(np.inf)
+    o_.append([0.5, 0.0, -2.0]); d_.append([0.0, 0.0, 3.0]); m_.append(np.inf)            # un-normalised direction, on an edge
+    rays = c.make_rays(o_, d_, np.array(m_))
+    got = gpu.intersect(rays, mode=c.TRAVERSE_F32)
+    occ = gpu.intersects(rays, mode=c.TRAVERSE_F32)
+    n_prims = int(hs.desc.n_primitives)
+    assert np.all((got["prim"] == c.CRAY_NO_HIT) | (got["prim"] < n_prims))
+    assert np.all(got["prim"][n_regular:n_regular + 3] == c.CRAY_NO_HIT) and not occ[n_regular:n_regular + 3].any()
+    ref = gpu.intersect(rays[:n_regular], mode=c.TRAVERSE_FAST)
+    ref_occ = gpu.intersects(rays[:n_regular], mode=c.TRAVERSE_FAST)
+    same = got["prim"][:n_regular] == ref["prim"]
+    assert same.all(), f"{int((~same).sum())} regular rays differ from the parity mode"
+    assert np.array_equal(got["t"][:n_regular][same], ref["t"][same])
+    assert np.array_equal(occ[:n_regular], ref_occ)
+
+
+def test_f32_render_multi_entry_point():
+    """cray_render_multi accepts the F32 mode (one GPU is enough to go through the entry point)."""
+    hs = SCENES["test"][0]()
+    scenes_ = c.Scene.create_multi(hs, [0], build=F32_BUILD)
+    film, st = c.render_multi(scenes_, seed=0, sample_begin=0, sample_end=4, mode=c.TRAVERSE_F32)
+    ref, st_ref = scenes_[0].render(seed=0, sample_begin=0, sample_end=4, mode=c.TRAVERSE_FAST)
+    assert st.samples == st_ref.samples
+    assert rel_mse(film, ref) <= 1e-4
