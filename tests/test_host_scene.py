@@ -247,3 +247,14 @@ def test_ctypes_mirror_matches_the_header_layout():
               _abi.RAY_DTYPE.itemsize, _abi.HIT_DTYPE.itemsize, _abi.SURFACE_DTYPE.itemsize, C.sizeof(_abi.RenderStats), C.sizeof(_abi.SceneInfo),
               C.sizeof(_abi.BvhNodeDump)]
     assert n == len(mirror) and list(out[:n]) == mirror
+
+
+def test_ctypes_constants_match_the_header():
+    """Build flags, traversal modes and error codes of craytracer_b200/_abi.py are the header's."""
+    import re
+    header = open(os.path.join(ROOT, "include", "cray_b200.h")).read()
+    defines = {m.group(1): m.group(2) for m in re.finditer(r"#define\s+(CRAY_\w+)\s+\(?(-?\d+)u?\)?", header)}
+    assert (int(defines["CRAY_BUILD_EXACT"]), int(defines["CRAY_BUILD_FAST"]), int(defines["CRAY_BUILD_F32"])) == (_abi.BUILD_EXACT, _abi.BUILD_FAST, _abi.BUILD_F32)
+    modes = re.search(r"enum\s*\{\s*CRAY_TRAVERSE_EXACT\s*=\s*(\d+),\s*CRAY_TRAVERSE_FAST\s*=\s*(\d+),\s*CRAY_TRAVERSE_F32\s*=\s*(\d+)\s*\}", header)
+    assert tuple(int(g) for g in modes.groups()) == (_abi.TRAVERSE_EXACT, _abi.TRAVERSE_FAST, _abi.TRAVERSE_F32)
+    assert int(defines["CRAY_E_PARSE"]) == _abi.CRAY_E_PARSE
