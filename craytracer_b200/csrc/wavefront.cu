@@ -498,6 +498,9 @@ __global__ void __launch_bounds__(128) k_extend_exact(SceneView s, Pool p, const
 #ifndef CRAY_SHADE_PREFETCH
 #define CRAY_SHADE_PREFETCH 1
 #endif
+#ifndef CRAY_SHADE_STATE_PREFETCH
+#define CRAY_SHADE_STATE_PREFETCH 0
+#endif
 constexpr uint32_t kShadeThreads = CRAY_SHADE_THREADS;
 constexpr uint32_t kShadeKeys = 16;   // class (matte, glass, plastic, metal) x shape kind (3); 12 = miss; 13 = no path
 
@@ -515,6 +518,17 @@ __global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(cons
         uint32_t mine = 0xFFFFFFFFu, key = 13u;
         if (q < n_extend) {
             mine = p.extend_queue[q];
+#if CRAY_SHADE_STATE_PREFETCH
+            // the path state of this block's 256 slots is read after the sort by whichever thread gets the path: ask for the lines now
+            {
+                const double* const arrays[] = {p.ox, p.oy, p.oz, p.dx, p.dy, p.dz, p.L_r, p.L_g, p.L_b, p.beta_r, p.beta_g, p.beta_b, p.prev_bsdf_pdf, p.hit_t};
+#pragma unroll
+                for (int a = 0; a < 14; ++a) asm volatile("prefetch.global.L1 [%0];" ::"l"(arrays[a] + mine));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.state + mine));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.shuffled_rev + mine));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.hash + mine));
+            }
+#endif
             const uint32_t my_slot = p.hit_slot[mine];
             key = 12u;
             if (my_slot != CRAY_NO_HIT) {
