@@ -187,7 +187,7 @@ struct WideTuning {
 #endif
 constexpr int kWideMinBlocks = CRAY_WIDE_MIN_BLOCKS;
 #ifndef CRAY_WIDE_MIN_BLOCKS_ANY
-#define CRAY_WIDE_MIN_BLOCKS_ANY 8
+#define CRAY_WIDE_MIN_BLOCKS_ANY 9
 #endif
 constexpr int kWideMinBlocksAny = CRAY_WIDE_MIN_BLOCKS_ANY;   // the any-hit instantiation carries less state   // CTAs of 128 threads per SM the register allocation is held to
 #ifndef CRAY_WIDE_MIN_BLOCKS_F32
