@@ -140,6 +140,15 @@ void cray_host_scene_destroy(cray_host_scene*);
 /* line/column of the last CRAY_E_PARSE on this thread (Location, scene_parser.rs:1-11); 0:0 if none */
 void cray_last_error_location(uint32_t* line, uint32_t* column);
 
+/* Warnings gathered while reading a scene (unused keys, MTL problems, stand-in meshes). */
+uint64_t cray_host_scene_num_warnings(const cray_host_scene*);
+const char* cray_host_scene_warning(const cray_host_scene*, uint64_t i);
+/* The reference's repository does not ship two of its meshes (objs/xyzrgb_dragon.obj, objs/staircase/staircase.obj,
+ * .MISSING_LARGE_BLOBS).  A scene that names `file_name` and does not find it on disk gets a seeded procedural mesh instead:
+ * kind 0 = closed displaced tube of `triangles` triangles standing on y = -40 (the dragon's extent), kind 1 = interior with
+ * stairs using the materials of the staircase MTL.  Process-wide; without a registration a missing mesh is CRAY_E_IO. */
+void cray_register_standin_mesh(const char* file_name, int kind, uint64_t triangles, uint64_t seed);
+
 /* ---- device scene (S0) --------------------------------------------------------- */
 
 typedef struct cray_scene cray_scene;   /* opaque; owns all device memory on its GPU */

@@ -105,3 +105,49 @@ def test_cli_renders_a_scene_file_to_exr(tmp_path):
     out2 = tmp_path / "out2.exr"
     assert cli_main(["-s", str(scene_path), "--output", str(out2), "--spp", "2", "--mode", "exact"]) == 0
     assert read_exr(out2).shape == (40, 64, 3)
+
+
+# ---- the compiled command line (craytracer_b200/csrc/cli_main.cpp -> craytracer_b200/cray_b200), C ABI only ----
+
+CLI = os.path.join(ROOT, "craytracer_b200", "cray_b200")
+
+
+def test_compiled_cli_arguments_and_errors(tmp_path):
+    """The reference's flags (struct Cli, craytracer.rs:321-334); a parse error is logged with its location and, like the
+    reference's main (:346-355), is not a failing exit; without a device the render fails loudly (no CPU path)."""
+    res = subprocess.run([CLI, "--help"], capture_output=True, text=True)
+    assert res.returncode == 0 and all(flag in res.stdout for flag in ("--scene", "--output", "--seed", "--preview"))
+    res = subprocess.run([CLI], capture_output=True, text=True)
+    assert res.returncode == 2 and "--scene" in res.stderr
+    res = subprocess.run([CLI, "--scene", "x.cry", "--mode", "bogus"], capture_output=True, text=True)
+    assert res.returncode == 2
+    bad = tmp_path / "bad.cry"
+    bad.write_text("{ camera: Perspective { origin: Point(0,0,-5) target: Point(0,0,0) } }")
+    res = subprocess.run([CLI, "--scene", str(bad)], capture_output=True, text=True)
+    assert res.returncode == 0 and "[ERROR]" in res.stderr and f"{bad}:1:" in res.stderr
+    res = subprocess.run([CLI, "--scene", str(tmp_path / "missing.cry")], capture_output=True, text=True)
+    assert res.returncode == 1 and "[ERROR]" in res.stderr
+    good = tmp_path / "simple_small.cry"
+    good.write_text(scenes.simple(num_samples=1, width=32, height=20))
+    res = subprocess.run([CLI, "--scene", str(good), "--output", str(tmp_path / "o.exr")], capture_output=True, text=True,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert res.returncode == 1 and "no CUDA device" in res.stderr and not (tmp_path / "o.exr").exists()
+
+
+@pytest.mark.gpu
+def test_compiled_cli_renders_the_same_film_as_the_library(tmp_path):
+    text = scenes.simple(num_samples=3, width=64, height=40)
+    scene_path = tmp_path / "simple_small.cry"
+    scene_path.write_text(text)
+    out = tmp_path / "out.exr"
+    res = subprocess.run([CLI, "--scene", str(scene_path), "--output", str(out), "--seed", "5"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert "Scene constructed in" in res.stderr and "Rendering finished in" in res.stderr and f"Output written to {out}" in res.stderr
+    gpu = c.Scene(c.parse_scene(text))
+    ref, _ = gpu.render(seed=5, sample_begin=0, sample_end=3)
+    film = read_exr(out)
+    assert film.shape == (40, 64, 3)
+    assert np.array_equal(film, ref / np.float32(3))
+    out2 = tmp_path / "out2.exr"
+    res = subprocess.run([CLI, "-s", str(scene_path), "--output", str(out2), "--spp", "2", "--mode", "f32", "--preview"], capture_output=True, text=True)
+    assert res.returncode == 0 and read_exr(out2).shape == (40, 64, 3)
