@@ -125,13 +125,13 @@ SIGNATURES = {
     "cray_free": (None, [_P]),
     "cray_last_error": (C.c_char_p, []),
     "cray_version": (C.c_char_p, []),
+    "cray_host_scene_num_warnings": (C.c_uint64, [_P]),
+    "cray_host_scene_warning": (C.c_char_p, [_P, C.c_uint64]),
+    "cray_register_standin_mesh": (None, [C.c_char_p, C.c_int, C.c_uint64, C.c_uint64]),
 }
 # host-side helpers that are not part of the reference-facing header
 EXTRA_SIGNATURES = {
-    "cray_host_scene_num_warnings": (C.c_uint64, [_P]),
-    "cray_host_scene_warning": (C.c_char_p, [_P, C.c_uint64]),
     "cray_set_image_decoder": (None, [IMAGE_DECODER]),
-    "cray_register_standin_mesh": (None, [C.c_char_p, C.c_int, C.c_uint64, C.c_uint64]),
     "cray_clear_standin_meshes": (None, []),
     "cray_debug_transformation": (None, [C.c_int, _P, _P, _P]),
     "cray_debug_matrix_inverse": (C.c_int, [_P, _P]),
