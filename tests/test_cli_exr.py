@@ -112,6 +112,13 @@ def test_cli_renders_a_scene_file_to_exr(tmp_path):
 CLI = os.path.join(ROOT, "craytracer_b200", "cray_b200")
 
 
+@pytest.fixture(autouse=True, scope="module")
+def _compiled_cli_present():
+    """Built by __graft_entry__.build() / make beside the library; (re)build it here if a snapshot arrived without it."""
+    if not os.path.exists(CLI):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "craytracer_b200", "csrc"), "../cray_b200"], capture_output=True)
+
+
 def test_compiled_cli_arguments_and_errors(tmp_path):
     """The reference's flags (struct Cli, craytracer.rs:321-334); a parse error is logged with its location and, like the
     reference's main (:346-355), is not a failing exit; without a device the render fails loudly (no CPU path)."""
