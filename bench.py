@@ -59,11 +59,30 @@ def measured_peaks():
         return 6650.0, "fallback"
 
 
+ALGORITHMIC_BYTES_PER_VERTEX = 336  # path state 64 + 64, hit 16, shading attributes 60, material 64, two rays 64, texel 4
+
+
+def library_sha256():
+    import hashlib
+    from craytracer_b200 import _abi
+    path = os.environ.get("CRAY_B200_LIB", _abi.LIB_PATH)
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for chunk in iter(lambda: f.read(1 << 20), b""):
+            h.update(chunk)
+    return h.hexdigest()
+
+
 def profiled_traffic():
-    """dram bytes per launch of the extend kernel (k_wide_persistent<false>) from the committed ncu summary of this workload, if any."""
+    """DRAM bytes per launch of each kernel from the committed `ncu --set full` capture of this workload (tools/final_capture.sh
+    -> tools/kernel_traffic.py -> profiles/kernel_traffic.json).  The capture names the library it was taken on by sha256: if
+    that is not the library being timed now, the figures are not this binary's and nothing is reported (null)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "extend_traffic.json")) as f:
-            return json.load(f)
+        with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
+            data = json.load(f)
+        if data.get("library_sha256") != library_sha256():
+            return None
+        return data
     except Exception:
         return None
 
@@ -186,7 +205,8 @@ def cpu_baseline(hs, args, budget_s, threads=0):
     dt = time.time() - t0
     rays = int(counts[0] + counts[1])
     return orc, {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                 "sample": f"{spp} of {args.spp} spp of the same frame ({rays} rays in {dt:.1f} s); rates are spp-independent",
+                 "sample": f"{spp} of {args.spp} spp of the same frame ({rays} reference rays = Scene::intersect + Scene::intersects calls, in {dt:.1f} s); "
+                           "rates are spp-independent",
                  "samples_per_s": args.width * args.height * spp / dt}
 
 
@@ -214,7 +234,8 @@ def run_reference(args):
     dt = time.time() - t0
     value = rays / dt / 1e6
     sample = f"each step = {spp} of {args.spp} spp of the frame on {cores} host threads; rates are spp-independent"
-    line = {"impl": "reference", "metric": "Mrays/s on dragon.cry", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": "Mrays/s on dragon.cry", "value": value, "unit": "Mrays/s",
+            "value_counts": "reference rays = Scene::intersect + Scene::intersects calls (every one of them is traced by the CPU renderer)", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": WORKLOAD, "spp": args.spp, "max_depth": 8, "sampler": "sobol"},
             "samples_per_s": args.width * args.height * spp * args.steps / dt,
@@ -276,7 +297,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        totals = {"closest": 0, "shadow": 0, "launches": 0, "trace_ms": 0.0, "render_ms": 0.0, "iters": 0, "nan": 0, "shade_ms": 0.0, "shadow_ms": 0.0,
+        totals = {"closest": 0, "shadow": 0, "shadow_traced": 0, "contact": 0, "launches": 0, "trace_ms": 0.0, "render_ms": 0.0, "iters": 0, "nan": 0, "shade_ms": 0.0, "shadow_ms": 0.0,
                   "generate_ms": 0.0}
         start.record(stream)
         for k in range(args.steps):
@@ -285,6 +306,8 @@ def run_ours(args):
             totals["host_ms"] = totals.get("host_ms", 0.0) + (time.perf_counter() - t_host) * 1e3
             totals["closest"] += st.closest_rays
             totals["shadow"] += st.shadow_rays
+            totals["shadow_traced"] += st.shadow_rays_traced
+            totals["contact"] += st.contact_rays
             totals["launches"] += st.kernel_launches + (1 if rank == 0 else 0)
             totals["trace_ms"] += st.trace_ms
             totals["shade_ms"] += st.shade_ms
@@ -298,7 +321,7 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         ms = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device="cuda")
-        counts = torch.tensor([totals["closest"], totals["shadow"], totals["launches"]], dtype=torch.float64, device="cuda")
+        counts = torch.tensor([totals["closest"], totals["shadow"], totals["launches"], totals["shadow_traced"]], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(counts, op=dist.ReduceOp.SUM)
@@ -328,7 +351,12 @@ def run_ours(args):
                            "not the headline because a ray grazing an edge may find the neighbouring triangle (tests/test_gpu_f32_mode.py)"}
 
     if rank == 0:
+        # "reference rays": the Scene::intersect + Scene::intersects calls the reference makes for these samples (what the CPU arm
+        # counts too, so the two arms' values are the same quantity).  "traced rays": what this implementation traced -- a path
+        # vertex whose light sample cannot contribute (black contribution, all-specular material: the dragon is a conductor) makes
+        # the reference's Scene::intersects call but needs no ray here.
         rays = counts_dev[0] + counts_dev[1]
+        traced = counts_dev[0] + counts_dev[3]
         samples = args.width * args.height * args.spp * args.steps
         value = rays / ms_dev / 1e3
         peak, peak_kind = measured_peaks()
@@ -337,15 +365,28 @@ def run_ours(args):
         bytes_per_ray = ALGORITHMIC_BYTES_PER_RAY_F32 if args.mode == "f32" else ALGORITHMIC_BYTES_PER_RAY
         achieved = totals["closest"] * bytes_per_ray / (extend_ms * 1e-3) / 1e9 if extend_ms > 0 else 0.0
         traffic = profiled_traffic() if args.mode == "fast" else None
+        tk = (traffic or {}).get("kernels", {})
+
+        def other(kernel, units, unit_name, per_unit, ms, key):
+            got = units * per_unit / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            t = tk.get(key)
+            return {"kernel": kernel, "bound": "hbm", "achieved": got, "peak": peak, "unit": "GB/s", "frac": got / peak, "units": units, "unit_name": unit_name,
+                    "algorithmic_bytes_per_unit": per_unit, "kernel_ms": ms, "kernel_share_of_step": ms / max(totals["render_ms"], 1e-9),
+                    "traffic": t["dram_bytes_per_launch"] if t else None, "traffic_detail": t}
+
         line = {
             "metric": "Mrays/s on dragon.cry", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "spp": args.spp, "max_depth": 8, "sampler": "sobol", "traversal": args.mode, "parallelism": f"samples/{world}",
                        "l2": "per-step working set (triangle records 578 MB + 8-wide nodes 115 MB + shading records 924 MB) exceeds the 126 MB L2"},
+            "value_counts": "reference rays = Scene::intersect + Scene::intersects calls of the reference for the same samples (the CPU arm counts the same)",
+            "rays": {"reference_closest": counts_dev[0], "reference_shadow": counts_dev[1], "traced_shadow": counts_dev[3],
+                     "reference_mrays_per_s": value, "traced_mrays_per_s": traced / ms_dev / 1e3,
+                     "contact_rays_in_reference_order": totals["contact"]},
             "samples_per_s": samples / (ms_dev * 1e-3),
             "rays_per_sample": rays / samples,
             "e2e": {"value": (counts_e2e[0] + counts_e2e[1]) / ms_e2e / 1e3, "unit": "Mrays/s", "h2d_bytes_per_step": job_bytes, "d2h_bytes_per_step": n_film * 4,
-                    "samples_per_s": samples / (ms_e2e * 1e-3),
+                    "samples_per_s": samples / (ms_e2e * 1e-3), "traced_mrays_per_s": (counts_e2e[0] + counts_e2e[3]) / ms_e2e / 1e3,
                     "note": "cray_render through the C ABI with a host film buffer every step (N>1: device film + NCCL reduce + copy to pinned host memory); "
                             "the scene is resident like the reference's &Scene, so the per-step host->device input is the job description only; "
                             "scene upload is reported under setup.upload_ms"},
@@ -353,13 +394,20 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_wide_persistent<false, ExtendSource" + (", true" if args.mode == "f32" else "") + "> (closest-hit traversal, 8-wide BVH)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_kind, "algorithmic_bytes_per_ray": bytes_per_ray,
                          "rays_in_kernel": totals["closest"], "kernel_ms": extend_ms, "kernel_share_of_step": extend_ms / max(totals["render_ms"], 1e-9),
-                         "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "traffic_detail": traffic},
+                         "traffic": tk["extend"]["dram_bytes_per_launch"] if "extend" in tk else None, "traffic_detail": tk.get("extend"),
+                         "traffic_capture": {k: v for k, v in (traffic or {}).items() if k != "kernels"} or None},
+            "other_kernels": [
+                other("k_shade (one path vertex: emission, light sample, BSDF sample, Russian roulette)", totals["closest"], "path vertices", ALGORITHMIC_BYTES_PER_VERTEX,
+                      totals["shade_ms"], "shade"),
+                other("k_wide_persistent<true, ShadowSource> (any-hit traversal of the traced shadow rays)", totals["shadow_traced"], "traced shadow rays",
+                      ALGORITHMIC_BYTES_PER_RAY, totals["shadow_ms"], "shadow")],
             "stage_ms_per_step": {"extend": totals["trace_ms"] / args.steps, "shade": totals["shade_ms"] / args.steps, "shadow": totals["shadow_ms"] / args.steps,
                                   "generate": totals["generate_ms"] / args.steps, "render_call": totals["render_ms"] / args.steps, "host_step": totals["host_ms"] / args.steps,
                                   "iterations": totals["iters"] / args.steps},
             "clocks": clocks,
             "setup": {"parse_and_standin_s": parse_s, "bvh_build_ms": scene.info.bvh_build_ms, "upload_ms": scene.info.upload_ms, "scene_create_s": create_s,
-                      "wide_nodes": scene.info.wide_nodes, "wide_depth": scene.info.wide_depth, "triangles": hs.desc.n_triangles},
+                      "wide_nodes": scene.info.wide_nodes, "wide_depth": scene.info.wide_depth, "triangles": hs.desc.n_triangles,
+                      "contact_nodes": scene.info.contact_nodes, "contact_primitives": scene.info.contact_primitives},
             "dropped_samples": totals["nan"],
         }
         if f32_leg:

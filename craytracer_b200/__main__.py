@@ -57,9 +57,11 @@ def main(argv=None):
     film = film / np.float32(max(spp, 1))  # pixels /= num_samples (craytracer.rs:253-259)
     stats = [st]
     dt = time.time() - t0
-    rays = sum(s.closest_rays + s.shadow_rays for s in stats)
+    rays = sum(s.closest_rays + s.shadow_rays for s in stats)          # the reference's Scene::intersect + intersects calls
+    traced = sum(s.closest_rays + s.shadow_rays_traced for s in stats)  # rays traced here (a light sample that cannot contribute needs none)
     dropped = sum(s.nan_samples for s in stats)
-    print(f"[INFO] Rendering finished in {dt:.3f}s ({rays / max(dt, 1e-9) / 1e6:.1f} Mrays/s, {sc0.width * sc0.height * spp / max(dt, 1e-9) / 1e6:.1f} Msamples/s"
+    print(f"[INFO] Rendering finished in {dt:.3f}s ({rays / max(dt, 1e-9) / 1e6:.1f} M reference rays/s, {traced / max(dt, 1e-9) / 1e6:.1f} M traced rays/s, "
+          f"{sc0.width * sc0.height * spp / max(dt, 1e-9) / 1e6:.1f} Msamples/s"
           + (f", {dropped} samples dropped where the reference would assert" if dropped else "") + ")", file=sys.stderr)
     write_exr(args.output, film)
     print(f"[INFO] Wrote {args.output}", file=sys.stderr)

@@ -76,14 +76,14 @@ class SceneDesc(C.Structure):
 class RenderStats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("nan_samples", C.c_uint64),
                 ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("render_ms", C.c_double), ("trace_ms", C.c_double),
-                ("shadow_ms", C.c_double), ("shade_ms", C.c_double), ("generate_ms", C.c_double)]
+                ("shadow_ms", C.c_double), ("shade_ms", C.c_double), ("generate_ms", C.c_double), ("shadow_rays_traced", C.c_uint64), ("contact_rays", C.c_uint64)]
 
 
 class SceneInfo(C.Structure):
     _fields_ = [("n_primitives", C.c_uint64), ("n_lights", C.c_uint64), ("exact_nodes", C.c_uint64), ("exact_bytes", C.c_uint64),
                 ("wide_nodes", C.c_uint64), ("wide_bytes", C.c_uint64), ("leaf_prim_bytes", C.c_uint64), ("wide_depth", C.c_uint64),
                 ("width", C.c_uint32), ("height", C.c_uint32), ("max_depth", C.c_uint32), ("num_samples", C.c_uint32),
-                ("bvh_build_ms", C.c_double), ("upload_ms", C.c_double)]
+                ("bvh_build_ms", C.c_double), ("upload_ms", C.c_double), ("contact_nodes", C.c_uint64), ("contact_primitives", C.c_uint64)]
 
 
 class BvhNodeDump(C.Structure):
@@ -138,6 +138,7 @@ EXTRA_SIGNATURES = {
     "cray_debug_camera_matrices": (None, [C.POINTER(CameraDesc), _P]),
     "cray_debug_check_wide_bvh": (C.c_int, [C.POINTER(SceneDesc), _P]),
     "cray_debug_wide_stats": (C.c_int, [_P]),
+    "cray_debug_find_contacts": (C.c_int, [C.POINTER(SceneDesc), _P, _P]),
     "cray_debug_tokenize": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     "cray_debug_parse_raw_value": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
 }

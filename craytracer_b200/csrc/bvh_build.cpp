@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <thread>
 
 #include "host_math.hpp"
@@ -370,6 +371,81 @@ void build_reference_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads
     out.error = top.error;
     splice(top, tasks, out);
     timer.mark("splice");
+}
+
+// ---- planar contact analysis (see bvh_build.hpp) ------------------------------------------------------------------------
+
+void find_contacts(const cray_scene_desc& d, const RefBvh& ref, ContactInfo& out) {
+    PhaseTimer timer;
+    const size_t np = (size_t)d.n_primitives, nn = ref.nodes.size();
+    out = ContactInfo{};
+    out.node_flags.assign(nn, 0);
+    out.prim_flag.assign(np, 0);
+    if (nn == 0) return;
+    // a hit location o + d * t carries a few ulps of the largest coordinate along the path
+    double big = 1.0;
+    for (int a = 0; a < 3; ++a) {
+        big = std::max(big, std::max(std::fabs(ref.bounds.lo[a]), std::fabs(ref.bounds.hi[a])));
+        big = std::max(big, std::fabs(d.camera.origin[a]));
+    }
+    const double noise = 16.0 * 2.220446049250313e-16 * big;
+    out.noise = noise;
+    const double grow = kContactTol + noise;
+    std::unique_ptr<std::atomic<uint8_t>[]> marked(new std::atomic<uint8_t>[nn]);
+    for (size_t i = 0; i < nn; ++i) marked[i].store(0, std::memory_order_relaxed);
+    const unsigned threads = std::max(1u, std::thread::hardware_concurrency());
+    std::atomic<size_t> next{0};
+    constexpr size_t kBatch = 4096;
+    auto run = [&]() {
+        std::vector<uint32_t> stack;
+        for (;;) {
+            const size_t b0 = next.fetch_add(kBatch);
+            if (b0 >= np) break;
+            for (size_t p = b0; p < std::min(np, b0 + kBatch); ++p) {
+                const Box3 pb = primitive_bounds(d, p);
+                bool planar[3], any = false;
+                for (int a = 0; a < 3; ++a) { planar[a] = pb.hi[a] - pb.lo[a] <= kPlanarThickness; any |= planar[a]; }
+                if (!any) continue;
+                stack.clear();
+                stack.push_back(0u);
+                while (!stack.empty()) {
+                    const uint32_t ni = stack.back();
+                    stack.pop_back();
+                    const BinNode& n = ref.nodes[ni];
+                    bool overlap = true;
+                    for (int a = 0; a < 3; ++a) overlap &= n.box.lo[a] - grow <= pb.hi[a] && n.box.hi[a] + grow >= pb.lo[a];
+                    if (!overlap) continue;
+                    for (int a = 0; a < 3; ++a) {
+                        if (!planar[a] || !(n.box.hi[a] - n.box.lo[a] > kThinNode)) continue;
+                        // some point of the primitive (its plane, give or take the rounding of a hit location) lies outside this
+                        // face by no more than the reference's epsilon
+                        const bool lo_face = n.box.lo[a] > pb.lo[a] - noise && n.box.lo[a] <= pb.hi[a] + grow;
+                        const bool hi_face = n.box.hi[a] < pb.hi[a] + noise && n.box.hi[a] >= pb.lo[a] - grow;
+                        if (lo_face || hi_face) {
+                            marked[ni].store(1, std::memory_order_relaxed);
+                            // (no path ray ever leaves an area light: its black matte ends the path and cancels the light sample, primitive.rs:43-46)
+                            if (d.primitives[p].area_light < 0) out.prim_flag[p] = 1;
+                        }
+                    }
+                    if (n.axis != 3) { stack.push_back(n.b); stack.push_back(n.a); }
+                }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < threads && (size_t)t * kBatch < np; ++t) pool.emplace_back(run);
+    run();
+    for (auto& th : pool) th.join();
+    // children follow their parents in the pre-order array: a reverse sweep sees them first
+    for (size_t i = nn; i-- > 0;) {
+        const BinNode& n = ref.nodes[i];
+        uint8_t f = marked[i].load(std::memory_order_relaxed) ? (CONTACT_NODE | CONTACT_BELOW) : 0;
+        if (n.axis != 3) f |= (out.node_flags[n.a] | out.node_flags[n.b]) & CONTACT_BELOW;
+        out.node_flags[i] = f;
+        out.n_nodes += f & CONTACT_NODE;
+    }
+    for (uint8_t f : out.prim_flag) out.n_prims += f;
+    timer.mark("planar contact analysis");
 }
 
 // ---- 8-wide collapse ----------------------------------------------------------------------------------

@@ -72,4 +72,28 @@ struct WideBvh {
 };
 void collapse_to_wide(const cray_scene_desc& d, const RefBvh& ref, WideBvh& out);
 
+// ---- planar contact (the reference's false box misses, SURVEY A-4b) -------------------------------------------------------
+//
+// Bvh::intersect / intersects visit a node iff `bounds.intersects(ray) || bounds.contains(origin)` (bvh.rs:70,:117), and
+// Bounds::intersects (bounds.rs:62-88) accepts only if the slab entry OR exit distance lies in (1e-9, ray.max_distance).  A ray
+// whose origin lies OUTSIDE a box by no more than 1e-9 (entry <= 1e-9, not "contained") and that ends inside the box -- or has
+// already found a hit nearer than the box's exit -- culls the whole subtree: the "box shaped hole" of scenes/rounding-error.cry.
+// Only origins in that outer shell of some node box can make the reference's result differ from a conservative traversal's, and
+// origins land there systematically only where a planar primitive coincides with a face of a node box (a floor at the root
+// box's minimum, a ground plane under a resting sphere).  find_contacts marks those boxes and primitives at build time; at
+// run time a ray that leaves a marked primitive is tested against the marked boxes (traverse.cuh: origin_in_contact_shell)
+// and, if it starts in such a shell, is traced by the reference-order traversal instead of the wide one.
+constexpr double kContactTol = 1.001e-9;       // EPSILON (constants.rs:1) for a unit direction, with margin
+constexpr double kPlanarThickness = 1e-5;      // a primitive whose box is thinner than this on an axis is planar on it
+constexpr double kThinNode = 2.5e-9;           // node boxes thinner than this on the axis hold only geometry in the plane itself
+enum : uint8_t { CONTACT_NODE = 1, CONTACT_BELOW = 2 };
+
+struct ContactInfo {
+    std::vector<uint8_t> node_flags;   // per binary node: CONTACT_NODE | CONTACT_BELOW (the node or a descendant is marked)
+    std::vector<uint8_t> prim_flag;    // per primitive: rays leaving it can start in the outer shell of a marked box
+    uint64_t n_nodes = 0, n_prims = 0;
+    double noise = 0.0;                // absolute rounding allowance for computed hit locations
+};
+void find_contacts(const cray_scene_desc& d, const RefBvh& ref, ContactInfo& out);
+
 }  // namespace cray

@@ -190,6 +190,21 @@ void cray_debug_camera_matrices(const cray_camera_desc* c, double* out32) {
     std::memcpy(out32 + 16, wfc.fwd.m, 16 * sizeof(double));
 }
 
+// The planar-contact analysis of bvh_build.hpp on the host only (no device): out[0] = marked node boxes, out[1] = marked primitives,
+// out[2] = binary nodes; prim_flags (optional, n_primitives bytes) receives the per-primitive marks.
+int cray_debug_find_contacts(const cray_scene_desc* desc, uint64_t* out3, uint8_t* prim_flags) {
+    using namespace cray;
+    if (!desc || !out3) { set_error("bad arguments"); return CRAY_E_INVALID; }
+    RefBvh ref;
+    build_reference_bvh(*desc, ref);
+    if (!ref.error.empty()) { set_error(ref.error); return CRAY_E_BVH; }
+    ContactInfo info;
+    find_contacts(*desc, ref, info);
+    out3[0] = info.n_nodes; out3[1] = info.n_prims; out3[2] = ref.nodes.size();
+    if (prim_flags) std::memcpy(prim_flags, info.prim_flag.data(), info.prim_flag.size());
+    return CRAY_OK;
+}
+
 // Structural check of the 8-wide BVH against the reference binary tree it was collapsed from (host only):
 // every primitive exactly once, every quantised child box encloses the exact f64 box of the subtree (or the single
 // primitive) it stands for.  out[0..3] = wide nodes, depth, interior children, leaf children.

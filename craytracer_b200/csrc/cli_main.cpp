@@ -15,6 +15,8 @@
 #include <string>
 #include <vector>
 
+#include <sys/stat.h>
+
 #include "../../include/cray_b200.h"
 
 namespace {
@@ -72,12 +74,19 @@ int main(int argc, char** argv) {
     cray_register_standin_mesh("objs/xyzrgb_dragon.obj", 0, 7219045ull, 0);
     cray_register_standin_mesh("objs/staircase/staircase.obj", 1, 1500000ull, 0);
 
-    // mesh paths are relative to the directory the reference is run from; default: the scene file's parent directory
+    // Mesh paths are relative to the directory the reference is run from (its repository root).  Without --base-dir: the first of
+    // the current directory, the scene file's parent directory and the packaged assets (<parent>/assets) that has an objs/
+    // directory -- the same search as `python -m craytracer_b200`.
     std::string base = args.base_dir;
     if (base.empty()) {
         const size_t slash = args.scene.find_last_of('/');
         const std::string dir = slash == std::string::npos ? "." : args.scene.substr(0, slash);
-        base = dir + "/..";
+        const std::string candidates[] = {".", dir + "/..", dir, dir + "/../assets", "assets"};
+        base = candidates[1];
+        for (const std::string& c : candidates) {
+            struct stat st{};
+            if (::stat((c + "/objs").c_str(), &st) == 0 && S_ISDIR(st.st_mode)) { base = c; break; }
+        }
     }
     cray_host_scene* hs = nullptr;
     int rc = cray_host_scene_load(args.scene.c_str(), base.c_str(), &hs);
@@ -116,9 +125,11 @@ int main(int argc, char** argv) {
         if (spp)
             for (float& p : pixels) p /= (float)spp;  // pixels /= num_samples (craytracer.rs:253-259)
         const double dt = seconds_since(t_render);
-        const double rays = (double)stats.closest_rays + (double)stats.shadow_rays;
-        std::fprintf(stderr, "[INFO] Rendering finished in %.3fs (%.1f Mrays/s, %.1f Msamples/s", seconds_since(start), rays / dt / 1e6,
-                     (double)width * height * spp / dt / 1e6);
+        // "reference rays": the Scene::intersect + Scene::intersects calls the reference makes for these samples; "traced": the rays this
+        // implementation traced (a light sample that cannot contribute needs no shadow ray)
+        const double rays = (double)stats.closest_rays + (double)stats.shadow_rays, traced = (double)stats.closest_rays + (double)stats.shadow_rays_traced;
+        std::fprintf(stderr, "[INFO] Rendering finished in %.3fs (%.1f M reference rays/s, %.1f M traced rays/s, %.1f Msamples/s", seconds_since(start), rays / dt / 1e6,
+                     traced / dt / 1e6, (double)width * height * spp / dt / 1e6);
         if (stats.nan_samples) std::fprintf(stderr, ", %llu samples dropped where the reference would assert", (unsigned long long)stats.nan_samples);
         std::fputs(")\n", stderr);
         rc = cray_write_exr(args.output.c_str(), width, height, pixels.data());

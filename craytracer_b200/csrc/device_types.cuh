@@ -16,7 +16,7 @@ enum : uint32_t { PRIM_SPHERE = CRAY_SHAPE_SPHERE, PRIM_TRIANGLE = CRAY_SHAPE_TR
 struct alignas(16) LeafPrim {
     double d[9];
     uint32_t prim;   // index in reference primitive order
-    uint32_t kind;   // PRIM_* | shade class << 8 (k_shade groups paths by it) | disk: index << 16, triangle: kKindFlatTriangle
+    uint32_t kind;   // PRIM_* | shade class << 8 (k_shade groups paths by it) | disk: index << 16, triangle: kKindFlatTriangle | kKindContact
 };
 static_assert(sizeof(LeafPrim) == 80, "LeafPrim layout");
 
@@ -47,6 +47,10 @@ struct alignas(32) TriShade {
 };
 static_assert(sizeof(TriShade) == 128, "TriShade layout");
 constexpr uint32_t kKindFlatTriangle = 1u << 16;  // LeafPrim::kind flag: n01 and n02 are all +0.0 (no vertex normals)
+// LeafPrim::kind flag: the primitive is planar and coincides with a face of some BVH node box, so a ray leaving it may start in the
+// outer shell of that box, where the reference's box test culls it (bvh_build.hpp "planar contact")
+constexpr uint32_t kKindContact = 1u << 31;
+CRAY_HD uint32_t disk_index(uint32_t kind) { return (kind >> 16) & 0x7FFFu; }
 
 enum : uint32_t { LOBE_LAMBERTIAN = 0, LOBE_OREN_NAYAR = 1, LOBE_CONDUCTOR = 2, LOBE_SPECULAR_BRDF = 3, LOBE_SPECULAR_BTDF = 4, LOBE_FRESNEL_SPECULAR = 5 };
 
@@ -88,6 +92,8 @@ struct SceneView {
     const WideNode* wide_nodes;
     const LeafPrim* wide_prims;      // wide leaf order
     const uint32_t* rank_of_prim;    // primitive -> rank in the reference leaf order (exact-t tie breaking)
+    const uint32_t* wide_slot_of_prim;  // primitive -> wide leaf slot (hits of the reference-order traversal inside the fast mode)
+    const uint8_t* bin_contact;      // per binary node: CONTACT_NODE | CONTACT_BELOW (bvh_build.hpp); null when no node is marked
     const Tri32* wide_tris32;        // F32 mode: f32 triangles in wide leaf order (null unless CRAY_BUILD_F32)
     const DiskXf* disks;
     // shading

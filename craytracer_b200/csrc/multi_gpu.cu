@@ -5,8 +5,8 @@
 // NCCL is resolved at run time (dlopen): the library has no link-time dependency on it, and single-GPU users never load it.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
-#include <nccl.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
@@ -16,6 +16,15 @@
 #include "scene_device.hpp"
 
 extern "C" float* cray_scene_film_f32(cray_scene* sc);  // wavefront.cu: the scene's device staging film (W*H*3 f32)
+
+// The handful of NCCL declarations used below, spelled out so that the library builds where the NCCL headers are absent (NCCL is
+// only ever dlopen'd); values as in nccl.h 2.x.
+extern "C" {
+typedef struct ncclComm* ncclComm_t;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclSum = 0 } ncclRedOp_t;
+typedef enum { ncclFloat = 7 } ncclDataType_t;
+}
 
 namespace cray {
 namespace {
@@ -49,9 +58,14 @@ NcclApi& nccl() {
     return api;
 }
 
-// one communicator clique per device list, created on first use and kept for the life of the process
+// one communicator clique per device list, created on first use and kept for the life of the process; its mutex is held across a
+// whole group of collectives, so two callers never issue on the same communicators at once
+struct Clique {
+    std::vector<ncclComm_t> comms;
+    std::mutex busy;
+};
 std::mutex g_comm_mutex;
-std::map<std::vector<int>, std::vector<ncclComm_t>> g_comms;
+std::map<std::vector<int>, Clique> g_comms;
 
 int nccl_fail(ncclResult_t r, const char* what) {
     set_error(std::string("NCCL error: ") + nccl().GetErrorString(r) + " in " + what);
@@ -98,7 +112,7 @@ extern "C" int cray_render_multi(cray_scene* const* scenes, int n, int mode, uin
 
     std::vector<int> devices(n);
     for (int k = 0; k < n; ++k) devices[k] = scenes[k]->device;
-    std::vector<ncclComm_t> comms;
+    Clique* clique = nullptr;
     {
         std::lock_guard<std::mutex> lock(g_comm_mutex);
         auto it = g_comms.find(devices);
@@ -106,10 +120,13 @@ extern "C" int cray_render_multi(cray_scene* const* scenes, int n, int mode, uin
             std::vector<ncclComm_t> fresh(n);
             ncclResult_t r = api.CommInitAll(fresh.data(), n, devices.data());
             if (r != ncclSuccess) return nccl_fail(r, "ncclCommInitAll");
-            it = g_comms.emplace(devices, fresh).first;
+            it = g_comms.try_emplace(devices).first;  // (std::map nodes never move: the pointer stays valid)
+            it->second.comms = fresh;
         }
-        comms = it->second;
+        clique = &it->second;
     }
+    std::lock_guard<std::mutex> busy(clique->busy);
+    const std::vector<ncclComm_t>& comms = clique->comms;
     const size_t count = (size_t)scenes[0]->info.width * scenes[0]->info.height * 3;
     ncclResult_t r = api.GroupStart();
     if (r != ncclSuccess) return nccl_fail(r, "ncclGroupStart");
@@ -130,6 +147,7 @@ extern "C" int cray_render_multi(cray_scene* const* scenes, int n, int mode, uin
         *stats = st[0];
         for (int k = 1; k < n; ++k) {
             stats->samples += st[k].samples; stats->closest_rays += st[k].closest_rays; stats->shadow_rays += st[k].shadow_rays;
+            stats->shadow_rays_traced += st[k].shadow_rays_traced; stats->contact_rays += st[k].contact_rays;
             stats->nan_samples += st[k].nan_samples; stats->kernel_launches += st[k].kernel_launches;
             stats->iterations = std::max(stats->iterations, st[k].iterations);
             stats->render_ms = std::max(stats->render_ms, st[k].render_ms);  // GPUs run side by side: the slowest one is the frame

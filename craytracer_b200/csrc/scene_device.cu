@@ -162,7 +162,7 @@ int validate(const cray_scene_desc* d) {
     if (d->n_primitives == 0) { set_error("scene has no primitives"); return CRAY_E_INVALID; }
     if (d->n_lights == 0) { set_error("No lights in the scene."); return CRAY_E_INVALID; }  // scene_parser.rs:1103
     if (d->n_primitives >= 0xFFFFFFF0ull) { set_error("too many primitives"); return CRAY_E_INVALID; }
-    if (d->n_disks > 0xFFFFull) { set_error("more than 65535 disks"); return CRAY_E_UNSUPPORTED; }
+    if (d->n_disks > 0x7FFFull) { set_error("more than 32767 disks"); return CRAY_E_UNSUPPORTED; }
     if (d->camera.width == 0 || d->camera.height == 0 || d->camera.width > 65535 || d->camera.height > 65535) { set_error("film size out of range"); return CRAY_E_INVALID; }
     for (uint64_t i = 0; i < d->n_primitives; ++i) {
         const cray_primitive_desc& p = d->primitives[i];
@@ -189,7 +189,8 @@ struct HostBuild {
     WideBvh wide;
     std::vector<LeafPrim> bin_prims, wide_prims;
     std::vector<Tri32> wide_tris32;
-    std::vector<uint32_t> rank_of_prim;
+    std::vector<uint32_t> rank_of_prim, wide_slot_of_prim;
+    ContactInfo contact;
     std::vector<DiskXf> disks;
     std::vector<TriShade> tri_shade;
     std::vector<DevMaterial> materials;
@@ -218,6 +219,8 @@ int build_host_side(const cray_scene_desc* d, uint32_t build_flags, HostBuild& h
         if (wide.depth >= (uint32_t)kWideStackLimit) { set_error("wide BVH deeper than the traversal stack"); return CRAY_E_BVH; }
         if (d->n_primitives >= (1ull << 27)) { set_error("more than 2^27 primitives: the fast traversal's queue entries hold 27-bit leaf slots"); return CRAY_E_UNSUPPORTED; }
     }
+    // planar contact (bvh_build.hpp): which boxes and primitives can produce the reference's false box misses
+    if (build_flags & CRAY_BUILD_FAST) find_contacts(*d, ref, hb.contact);
     hb.build_ms = ms_since(t0);
     PhaseTimer timer;
     const size_t np = (size_t)d->n_primitives;
@@ -226,6 +229,8 @@ int build_host_side(const cray_scene_desc* d, uint32_t build_flags, HostBuild& h
     std::vector<LeafPrim>& wide_prims = hb.wide_prims;
     std::vector<uint32_t>& rank_of_prim = hb.rank_of_prim;
     bin_prims.resize(np); wide_prims.resize(wide.prim_order.size()); rank_of_prim.resize(np);
+    if (!wide_prims.empty()) hb.wide_slot_of_prim.resize(np);
+    const std::vector<uint8_t>& contact_prim = hb.contact.prim_flag;
     std::vector<Tri32>& wide_tris32 = hb.wide_tris32;
     if (build_flags & CRAY_BUILD_F32) wide_tris32.resize(wide_prims.size());
     {
@@ -235,7 +240,12 @@ int build_host_side(const cray_scene_desc* d, uint32_t build_flags, HostBuild& h
             for (size_t i = t; i < np; i += nt) {
                 bin_prims[i] = make_leaf_prim(*d, ref.prim_order[i]);
                 rank_of_prim[ref.prim_order[i]] = (uint32_t)i;
-                if (!wide_prims.empty()) wide_prims[i] = make_leaf_prim(*d, wide.prim_order[i]);
+                if (!wide_prims.empty()) {
+                    const uint32_t prim = wide.prim_order[i];
+                    wide_prims[i] = make_leaf_prim(*d, prim);
+                    if (!contact_prim.empty() && contact_prim[prim]) wide_prims[i].kind |= kKindContact;
+                    hb.wide_slot_of_prim[prim] = (uint32_t)i;
+                }
                 if (!wide_tris32.empty()) wide_tris32[i] = make_tri32(wide_prims[i]);
             }
         };
@@ -392,6 +402,8 @@ int upload_scene(const HostBuild& hb, const cray_scene_desc* d, int device, cray
     UP(hb.wide_prims, v.wide_prims);
     UP(hb.wide_tris32, v.wide_tris32);
     UP(hb.rank_of_prim, v.rank_of_prim);
+    UP(hb.wide_slot_of_prim, v.wide_slot_of_prim);
+    if (hb.contact.n_nodes) UP(hb.contact.node_flags, v.bin_contact);
     UP(hb.disks, v.disks);
     UP(hb.prims, v.prims);
     UP(hb.tri_shade, v.tri_shade);
@@ -425,6 +437,8 @@ int upload_scene(const HostBuild& hb, const cray_scene_desc* d, int device, cray
     info.wide_depth = hb.wide.depth;
     info.width = hb.cam.width; info.height = hb.cam.height;
     info.max_depth = d->max_depth; info.num_samples = d->num_samples;
+    info.contact_nodes = hb.contact.n_nodes;
+    info.contact_primitives = hb.contact.n_prims;
     info.bvh_build_ms = hb.build_ms;
     info.upload_ms = ms_since(t0);
     guard.s = nullptr;

@@ -278,7 +278,7 @@ __device__ __forceinline__ V3 shape_sample(const SceneView& s, const LeafPrim& s
         const double b1 = 1.0 - su_sqrt, b2 = sv * su_sqrt;
         return mk(sh.d[0], sh.d[1], sh.d[2]) + mk(sh.d[3], sh.d[4], sh.d[5]) * b1 + mk(sh.d[6], sh.d[7], sh.d[8]) * b2;
     }
-    const DiskXf& k = s.disks[sh.kind >> 16];
+    const DiskXf& k = s.disks[disk_index(sh.kind)];
     double x, y;
     sample_disk(su, sv, x, y);
     return xf_point(k.o2w, mk(x * k.radius, y * k.radius, 0.0));

@@ -114,7 +114,7 @@ __device__ __forceinline__ bool leaf_prim_closest(const SceneView& s, const Leaf
         return true;
     }
     double lx, ly, d2;
-    if (!disk_hit(s.disks[lp.kind >> 16], o, dir, ray_max, t, lx, ly, d2)) return false;
+    if (!disk_hit(s.disks[disk_index(lp.kind)], o, dir, ray_max, t, lx, ly, d2)) return false;
     ray_max = t; u = 0.0; v = 0.0;
     return true;
 }
@@ -128,7 +128,7 @@ __device__ __forceinline__ bool leaf_prim_any(const SceneView& s, const LeafPrim
         // Shape::intersects tests the object-space ray's range only (shape.rs:336-341)
         return sphere_hit(lp.d, o, dir, ray_max, t, a);
     }
-    return disk_hit(s.disks[lp.kind >> 16], o, dir, ray_max, t, a, b, c);
+    return disk_hit(s.disks[disk_index(lp.kind)], o, dir, ray_max, t, a, b, c);
 }
 
 // Spheres and disks of the wide-BVH closest-hit test below.  Out of line: scenes have a handful of them, and inlined their f64
@@ -222,7 +222,7 @@ __device__ __forceinline__ void surface_at(const SceneView& s, const LeafPrim& l
         normal = loc / radius;                                               // inverse-transpose of a translation is the identity
         return;
     }
-    const DiskXf& k = s.disks[lp.kind >> 16];  // shape.rs:283-308
+    const DiskXf& k = s.disks[disk_index(lp.kind)];  // shape.rs:283-308
     const V3 oo = xf_point(k.w2o, o);
     const V3 od = xf_vector(k.w2o, dir);
     const double lx = oo.x + od.x * t, ly = oo.y + od.y * t;

@@ -57,6 +57,37 @@ __device__ __forceinline__ bool traverse_exact(const SceneView& s, V3 o, V3 dir,
     return hit.slot != CRAY_NO_HIT;
 }
 
+// Does `o` lie in the outer shell of a marked node box (bvh_build.hpp "planar contact"): outside the box -- Bounds::contains
+// (bounds.rs:46-53) is false -- but by no more than `tol` on every axis, so that the slab entry distance of a ray of direction
+// length <= tol / 1e-9 can be <= 1e-9?  Only such rays can be culled by the reference's box test where a conservative traversal
+// would go on (bvh.rs:70,:117 with bounds.rs:62-88); the caller traces them with traverse_exact.  Walks only the part of the binary
+// tree that holds marked nodes and whose grown boxes contain `o`.
+__device__ __noinline__ bool origin_in_contact_shell(const SceneView& s, V3 o, double tol) {
+    if (!s.bin_contact) return false;
+    uint32_t stack[kExactStack];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        const uint32_t ni = stack[--sp];
+        const uint32_t flags = s.bin_contact[ni];
+        if (!(flags & CONTACT_BELOW)) continue;
+        const BinNode* np = s.bin_nodes + ni;
+        const int4* raw = reinterpret_cast<const int4*>(np);
+        BinNode n;
+        int4* dst = reinterpret_cast<int4*>(&n);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = __ldg(raw + i);
+        if (!(n.box.lo.x - tol <= o.x && n.box.lo.y - tol <= o.y && n.box.lo.z - tol <= o.z && n.box.hi.x + tol >= o.x && n.box.hi.y + tol >= o.y &&
+              n.box.hi.z + tol >= o.z))
+            continue;
+        if ((flags & CONTACT_NODE) && !bounds_contains(n.box, o)) return true;
+        if (n.axis != 3 && sp + 2 <= kExactStack) { stack[sp++] = n.b; stack[sp++] = n.a; }
+    }
+    return false;
+}
+// ... with the tolerance of a ray of direction `dir` (its largest component scales the reference's 1e-9)
+__device__ __forceinline__ double contact_tol(V3 dir) { return kContactTol * fmax(1.0, fmax(fabs(dir.x), fmax(fabs(dir.y), fabs(dir.z)))); }
+
 // Would the reference's depth-first traversal reach primitive `pa` before `pb` for this ray direction?
 // (Both given as ranks in the reference leaf order.)  Walks down from the root to their lowest common ancestor.
 __device__ __noinline__ bool reference_visits_first(const SceneView& s, uint32_t rank_a, uint32_t rank_b, V3 dir) {

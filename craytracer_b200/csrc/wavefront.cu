@@ -44,9 +44,13 @@ struct Pool {  // structure-of-arrays over `capacity` path slots
     double *beta_r, *beta_g, *beta_b, *L_r, *L_g, *L_b, *prev_bsdf_pdf;
     double *sdx, *sdy, *sdz, *smax, *sc_r, *sc_g, *sc_b;  // pending shadow ray (origin = ox,oy,oz) and its contribution
     uint32_t *id, *pixel, *hash, *shuffled_rev;    // job-relative sample id, film offset, sampler state
-    uint32_t* state;                               // state | bounces << 8 | specular << 16 | shadow_pending << 17 | bad << 18
-    uint32_t *extend_queue, *shadow_queue;         // slot indices with a ray to extend / a shadow ray to test this iteration
+    uint32_t* state;                               // state | bounces << 8 | specular << 16 | shadow_pending << 17 | bad << 18 | contact << 19
+    // slot indices with a ray to extend / a shadow ray to test this iteration.  Rays for the wide traversal fill a queue from the
+    // front; rays that start in a contact shell (state bit 19, fast and F32 modes) go to the reference-order traversal and fill the
+    // same array from the back (entry k at capacity - 1 - k): the two never meet, there is at most one entry per slot.
+    uint32_t *extend_queue, *shadow_queue;
 };
+constexpr uint32_t kStateContact = 1u << 19;
 
 struct Job {
     uint64_t seed;
@@ -65,9 +69,12 @@ struct Job {
 struct Counters {
     unsigned long long next_id;
     unsigned long long closest_rays, shadow_rays, nan_samples;
-    // per-iteration part, cleared before every k_generate
-    unsigned long long n_extend, n_shadow;          // queue lengths
+    unsigned long long shadow_traced;               // shadow rays that were actually queued and traced (sum of the queue lengths)
+    unsigned long long contact_rays;                // rays (closest + shadow) routed to the reference-order traversal in fast mode
+    // per-iteration part, rolled into the totals above and cleared by k_begin_iteration
+    unsigned long long n_extend, n_shadow;          // queue lengths (front part)
     unsigned long long extend_cursor, shadow_cursor;  // persistent-kernel fetch positions
+    unsigned long long n_extend_contact, n_shadow_contact;  // queue lengths (back part)
 };
 
 __device__ __forceinline__ uint32_t st_state(uint32_t s) { return s & 0xFFu; }
@@ -151,14 +158,16 @@ struct RayArraySource {  // S3: caller-provided cray_ray records
     cray_surface* surf;
     uint8_t* occluded;
     bool f32;
+    const uint32_t* index;  // the rays of this launch (k_classify_rays), or null for all of them
     __device__ __forceinline__ uint32_t self_slot(uint32_t) const { return CRAY_NO_HIT; }
     __device__ __forceinline__ float t_min32(V3 o, V3 d) const { return f32_unknown_origin_tmin(o, d); }
     __device__ __forceinline__ uint32_t load(uint64_t idx, V3& o, V3& d, double& ray_max) const {
-        const cray_ray r = rays[idx];
+        const uint32_t i = index ? index[idx] : (uint32_t)idx;
+        const cray_ray r = rays[i];
         o = mk(r.origin[0], r.origin[1], r.origin[2]);
         d = mk(r.direction[0], r.direction[1], r.direction[2]);
         ray_max = r.max_distance;
-        return (uint32_t)idx;
+        return i;
     }
     __device__ __forceinline__ void store_closest(const SceneView& s, uint32_t i, uint32_t slot, double t) const {
         Hit h;
@@ -323,24 +332,53 @@ __global__ void __launch_bounds__(128, F32 ? kWideMinBlocksF32 : (ANY ? kWideMin
 #endif
 }
 
-// ---- exact-mode kernels (reference binary BVH, one thread per ray) ------------------------------------------------------
+// ---- reference-order kernels (the reference's binary BVH, one thread per ray, grid-stride) ---------------------------------
+//
+// They serve the exact mode (every ray) and, inside the fast mode, the rays that start in a contact shell (bvh_build.hpp "planar
+// contact"): only this traversal reproduces the reference's box-test culls for them.  `index_back`: the rays of the launch are
+// listed from the back of an array of `n_all` entries (k_classify_rays); null: rays [0, n).
+constexpr unsigned kExactBlocks = 148 * 8;
 
-__global__ void __launch_bounds__(128) k_trace_closest_exact(SceneView s, const cray_ray* __restrict__ rays, uint64_t n, cray_hit* __restrict__ hits,
-                                                              cray_surface* __restrict__ surf) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const cray_ray r = rays[i];
-    Hit h;
-    const bool found = traverse_exact<false>(s, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), r.max_distance, h);
-    write_hit(s, s.bin_prims, r, h, true, found, i, hits, surf);
+__global__ void __launch_bounds__(128) k_trace_closest_exact(SceneView s, const cray_ray* __restrict__ rays, const unsigned long long* __restrict__ n_ptr, const uint32_t* __restrict__ index_back,
+                                                              uint64_t n_all, cray_hit* __restrict__ hits, cray_surface* __restrict__ surf) {
+    const uint64_t n = *n_ptr;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = index_back ? index_back[n_all - 1 - q] : q;
+        const cray_ray r = rays[i];
+        Hit h;
+        const bool found = traverse_exact<false>(s, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), r.max_distance, h);
+        write_hit(s, s.bin_prims, r, h, true, found, i, hits, surf);
+    }
 }
 
-__global__ void __launch_bounds__(128) k_trace_any_exact(SceneView s, const cray_ray* __restrict__ rays, uint64_t n, uint8_t* __restrict__ occluded) {
+__global__ void __launch_bounds__(128) k_trace_any_exact(SceneView s, const cray_ray* __restrict__ rays, const unsigned long long* __restrict__ n_ptr, const uint32_t* __restrict__ index_back,
+                                                          uint64_t n_all, uint8_t* __restrict__ occluded) {
+    const uint64_t n = *n_ptr;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = index_back ? index_back[n_all - 1 - q] : q;
+        const cray_ray r = rays[i];
+        Hit h;
+        occluded[i] = traverse_exact<true>(s, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), r.max_distance, h) ? 1 : 0;
+    }
+}
+
+// S3, fast mode, scenes with marked boxes: splits the batch into the rays the wide traversal may take (listed from the front of
+// `list`) and the rays that start in a contact shell (from the back).  counts[0] = front length, counts[2] = back length.
+__global__ void __launch_bounds__(128) k_classify_rays(SceneView s, const cray_ray* __restrict__ rays, uint64_t n, uint32_t* __restrict__ list, unsigned long long* counts) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const cray_ray r = rays[i];
-    Hit h;
-    occluded[i] = traverse_exact<true>(s, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), r.max_distance, h) ? 1 : 0;
+    const bool contact = origin_in_contact_shell(s, mk(r.origin[0], r.origin[1], r.origin[2]), contact_tol(mk(r.direction[0], r.direction[1], r.direction[2])));
+    const unsigned m = __activemask();
+    const unsigned mc = __ballot_sync(m, contact), mw = m & ~mc;
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned long long bw = 0, bc = 0;
+    if (mw && lane == (unsigned)(__ffs(mw) - 1)) bw = atomicAdd(&counts[0], (unsigned long long)__popc(mw));
+    if (mc && lane == (unsigned)(__ffs(mc) - 1)) bc = atomicAdd(&counts[2], (unsigned long long)__popc(mc));
+    if (mw) bw = __shfl_sync(m, bw, __ffs(mw) - 1);
+    if (mc) bc = __shfl_sync(m, bc, __ffs(mc) - 1);
+    if (contact) list[n - 1 - (bc + __popc(mc & ((1u << lane) - 1u)))] = (uint32_t)i;
+    else list[bw + __popc(mw & ((1u << lane) - 1u))] = (uint32_t)i;
 }
 
 // ---- wavefront kernels --------------------------------------------------------------------------------------
@@ -358,6 +396,16 @@ __device__ __forceinline__ void queue_append(unsigned long long* counter, uint32
     if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
     base = __shfl_sync(m, base, leader);
     queue[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
+// ... and to the back part of a queue of `capacity` entries (entry k sits at capacity - 1 - k)
+__device__ __forceinline__ void queue_append_back(unsigned long long* counter, uint32_t* queue, uint32_t capacity, uint32_t value) {
+    const unsigned m = __activemask();
+    const unsigned lane = threadIdx.x & 31u, leader = __ffs(m) - 1u;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    queue[capacity - 1u - (uint32_t)(base + __popc(m & ((1u << lane) - 1u)))] = value;
 }
 
 // Camera::sample + generate_ray camera.rs:131-162
@@ -399,6 +447,25 @@ __device__ __forceinline__ uint32_t block_rank_256(bool pred, uint32_t* s_warp, 
     return before + __popc(m & ((1u << lane) - 1u));
 }
 
+// The same for two disjoint predicates in one pass (counts packed 16 + 16 bits).
+__device__ __forceinline__ void block_rank2_256(bool pa, bool pb, uint32_t* s_warp, uint32_t& rank_a, uint32_t& rank_b, uint32_t& total_a, uint32_t& total_b) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned ma = __ballot_sync(0xFFFFFFFFu, pa), mb = __ballot_sync(0xFFFFFFFFu, pb);
+    if (lane == 0) s_warp[warp] = __popc(ma) | (__popc(mb) << 16);
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (unsigned w = 0; w < 8; ++w) {
+        const uint32_t c = s_warp[w];
+        before += w < warp ? c : 0u;
+        all += c;
+    }
+    __syncthreads();
+    total_a = all & 0xFFFFu; total_b = all >> 16;
+    rank_a = (before & 0xFFFFu) + __popc(ma & ((1u << lane) - 1u));
+    rank_b = (before >> 16) + __popc(mb & ((1u << lane) - 1u));
+}
+
 // One block = 256 consecutive path slots.  Finished paths are flushed by their own thread; the slots to refill are then
 // compacted, so that the camera-ray code (SipHash, four Sobol values, f64 camera transform) runs on full warps instead of on the
 // scattered third of the lanes whose path happened to end -- and the sample ids and the extend-queue range of the whole block
@@ -406,7 +473,7 @@ __device__ __forceinline__ uint32_t block_rank_256(bool pred, uint32_t* s_warp, 
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneView s, const __grid_constant__ Pool p, const __grid_constant__ Job job, Counters* counters) {
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_list[256];
-    __shared__ unsigned long long s_base[2];
+    __shared__ unsigned long long s_base[3];
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
     const bool in_range = i < p.capacity;
     uint32_t st = in_range ? p.state[i] : 0xFFu;  // 0xFF: no slot
@@ -466,23 +533,40 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneV
             p.state[slot] = SLOT_ACTIVE | (1u << 16);  // bounces = 0, is_specular_bounce = true (path_integrator.rs:50)
         }
     }
-    // every live slot has a ray to extend this iteration: the block's slots go to the queue in ascending order
+    // every live slot has a ray to extend this iteration: the block's slots go to the queue in ascending order -- to its back
+    // part if the ray starts in a contact shell (k_shade found out) and needs the reference-order traversal
     const bool live = st_state(st) == SLOT_ACTIVE || (empty && id_base + rank < job.n_total);
-    uint32_t n_live;
-    const uint32_t qrank = block_rank_256(live, s_warp, n_live);
-    if (threadIdx.x == 0 && n_live) s_base[1] = atomicAdd(&counters->n_extend, (unsigned long long)n_live);
+    const bool contact = live && (st & kStateContact) && st_state(st) == SLOT_ACTIVE;
+    uint32_t n_wide, n_contact, qrank, crank;
+    block_rank2_256(live && !contact, contact, s_warp, qrank, crank, n_wide, n_contact);
+    if (threadIdx.x == 0 && n_wide) s_base[1] = atomicAdd(&counters->n_extend, (unsigned long long)n_wide);
+    if (threadIdx.x == 32 && n_contact) s_base[2] = atomicAdd(&counters->n_extend_contact, (unsigned long long)n_contact);
     __syncthreads();
-    if (live) p.extend_queue[s_base[1] + qrank] = i;
+    if (contact) p.extend_queue[p.capacity - 1u - (uint32_t)(s_base[2] + crank)] = i;
+    else if (live) p.extend_queue[s_base[1] + qrank] = i;
 }
 
+// Start of a wavefront iteration: rolls the queue lengths of the previous one into the run's totals and clears the per-iteration
+// counters (one thread).
+__global__ void k_begin_iteration(Counters* c) {
+    c->shadow_traced += c->n_shadow + c->n_shadow_contact;
+    c->contact_rays += c->n_extend_contact + c->n_shadow_contact;
+    c->n_extend = 0; c->n_shadow = 0; c->extend_cursor = 0; c->shadow_cursor = 0; c->n_extend_contact = 0; c->n_shadow_contact = 0;
+}
+
+// BACK: the contact rays of the fast mode (back part of the queue); their hits are reported as wide leaf slots, which is what
+// k_shade reads in that mode.
+template <bool BACK>
 __global__ void __launch_bounds__(128) k_extend_exact(SceneView s, Pool p, const unsigned long long* __restrict__ n_ptr) {
-    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= *n_ptr) return;
-    const uint32_t i = p.extend_queue[q];
-    Hit h;
-    traverse_exact<false>(s, mk(p.ox[i], p.oy[i], p.oz[i]), mk(p.dx[i], p.dy[i], p.dz[i]), inf_f64(), h);
-    p.hit_slot[i] = h.slot;
-    p.hit_t[i] = h.t;
+    const uint64_t n = *n_ptr;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t i = p.extend_queue[BACK ? p.capacity - 1u - (uint32_t)q : (uint32_t)q];
+        Hit h;
+        traverse_exact<false>(s, mk(p.ox[i], p.oy[i], p.oz[i]), mk(p.dx[i], p.dy[i], p.dz[i]), inf_f64(), h);
+        if (BACK && h.slot != CRAY_NO_HIT) h.slot = s.wide_slot_of_prim[s.bin_prims[h.slot].prim];
+        p.hit_slot[i] = h.slot;
+        p.hit_t[i] = h.t;
+    }
 }
 
 // One iteration of the `while` loop of estimate_Li (path_integrator.rs:54-212) for one path.
@@ -509,7 +593,9 @@ __global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(cons
     __shared__ uint32_t s_count[kCells];
     __shared__ uint32_t s_warp_total[kCells / 32];
     __shared__ uint32_t s_order[kShadeThreads];
-    const uint64_t n_extend = counters->n_extend;
+    // the iteration's rays: the wide traversal's (front of the queue), then the reference-order traversal's (back of it)
+    const uint64_t n_front = counters->n_extend;
+    const uint64_t n_extend = n_front + counters->n_extend_contact;
     if ((uint64_t)blockIdx.x * kShadeThreads >= n_extend) return;  // whole block idle
     uint32_t i, slot;
     {
@@ -517,7 +603,7 @@ __global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(cons
         const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
         uint32_t mine = 0xFFFFFFFFu, key = 13u;
         if (q < n_extend) {
-            mine = p.extend_queue[q];
+            mine = p.extend_queue[q < n_front ? (uint32_t)q : p.capacity - 1u - (uint32_t)(q - n_front)];
 #if CRAY_SHADE_STATE_PREFETCH
             // the path state of this block's 256 slots is read after the sort by whichever thread gets the path: ask for the lines now
             {
@@ -653,6 +739,9 @@ __global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(cons
     // cannot contribute: it is not drawn (the reference's shadow ray, :141, is still counted).
     bool shadow_pending = false;
     warp_count(&counters->shadow_rays, true);
+    // Both rays of this vertex start at `location`.  If it lies in the outer shell of a marked node box, only the reference-order
+    // traversal reproduces what the reference's box test does to them (bvh_build.hpp "planar contact"); directions are unit vectors.
+    const bool contact = !job.exact && (lp.kind & kKindContact) && origin_in_contact_shell(s, location, kContactTol);
     if (!material.all_delta) {
         double light_sampler_pdf;
         // a single light is picked whatever the sample value is (the search of light.rs:203-211 ends at 0 for every u < 1)
@@ -676,7 +765,8 @@ __global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(cons
         // traced only when an unoccluded result could change L
         if (!is_black(contribution) || !is_finite3(contribution)) {
             shadow_pending = true;
-            queue_append(&counters->n_shadow, p.shadow_queue, i);
+            if (contact) queue_append_back(&counters->n_shadow_contact, p.shadow_queue, p.capacity, i);
+            else queue_append(&counters->n_shadow, p.shadow_queue, i);
             p.sdx[i] = ls.w_i.x; p.sdy[i] = ls.w_i.y; p.sdz[i] = ls.w_i.z;
             p.smax[i] = ls.shadow_max;
             p.sc_r[i] = contribution.r; p.sc_g[i] = contribution.g; p.sc_b[i] = contribution.b;
@@ -713,19 +803,22 @@ __global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(cons
         p.dx[i] = ss.w_i.x; p.dy[i] = ss.w_i.y; p.dz[i] = ss.w_i.z;
         p.beta_r[i] = beta.r; p.beta_g[i] = beta.g; p.beta_b[i] = beta.b;
         p.prev_bsdf_pdf[i] = bsdf_pdf;
-        p.state[i] = SLOT_ACTIVE | (next_bounces << 8) | ((ss.is_specular ? 1u : 0u) << 16) | ((shadow_pending ? 1u : 0u) << 17) | ((bad ? 1u : 0u) << 18);
+        p.state[i] = SLOT_ACTIVE | (next_bounces << 8) | ((ss.is_specular ? 1u : 0u) << 16) | ((shadow_pending ? 1u : 0u) << 17) | ((bad ? 1u : 0u) << 18) |
+                     (contact ? kStateContact : 0u);
     } else {
         p.state[i] = SLOT_DONE | (next_bounces << 8) | ((shadow_pending ? 1u : 0u) << 17) | ((bad ? 1u : 0u) << 18);
     }
 }
 
+template <bool BACK>
 __global__ void __launch_bounds__(128) k_shadow_exact(SceneView s, Pool p, const unsigned long long* __restrict__ n_ptr) {
-    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= *n_ptr) return;
-    const uint32_t i = p.shadow_queue[q];
-    Hit h;
-    if (!traverse_exact<true>(s, mk(p.ox[i], p.oy[i], p.oz[i]), mk(p.sdx[i], p.sdy[i], p.sdz[i]), p.smax[i], h)) {
-        p.L_r[i] += p.sc_r[i]; p.L_g[i] += p.sc_g[i]; p.L_b[i] += p.sc_b[i];
+    const uint64_t n = *n_ptr;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t i = p.shadow_queue[BACK ? p.capacity - 1u - (uint32_t)q : (uint32_t)q];
+        Hit h;
+        if (!traverse_exact<true>(s, mk(p.ox[i], p.oy[i], p.oz[i]), mk(p.sdx[i], p.sdy[i], p.sdz[i]), p.smax[i], h)) {
+            p.L_r[i] += p.sc_r[i]; p.L_g[i] += p.sc_g[i]; p.L_b[i] += p.sc_b[i];
+        }
     }
 }
 
@@ -748,7 +841,10 @@ struct PoolStorage {
     WideTuning tune{12, 8};
     unsigned shadow_blocks = 0;       // the any-hit instantiation needs fewer registers: its own occupancy
     unsigned f32_blocks = 0, f32_shadow_blocks = 0;  // F32 mode instantiations
-    unsigned long long* d_trace_counters = nullptr;  // {n, cursor} for the S3 entry points
+    unsigned long long* d_trace_counters = nullptr;  // {n, cursor, n of the reference-order launch} for the S3 entry points
+    uint32_t* d_trace_list = nullptr;                // S3 ray lists of k_classify_rays (grow only)
+    uint64_t trace_list_capacity = 0;
+    bool initialised = false;
     std::vector<cudaEvent_t> timers;                 // stage boundaries of every iteration of one render, reused across calls
 };
 
@@ -773,9 +869,9 @@ int resident_blocks(Kernel kernel, int* per_sm) {
 int ensure_pool(cray_scene* sc, uint32_t capacity) {
     auto* ps = static_cast<PoolStorage*>(sc->pool);
     if (!ps) { ps = new PoolStorage(); sc->pool = ps; }
-    if (!ps->d_counters) {
-        CRAY_CUDA(cudaMalloc(&ps->d_counters, sizeof(Counters)));
-        CRAY_CUDA(cudaMallocHost(&ps->h_counters, sizeof(Counters)));
+    if (!ps->initialised) {  // (set once everything below has succeeded: a retry after a failure starts over)
+        if (!ps->d_counters) CRAY_CUDA(cudaMalloc(&ps->d_counters, sizeof(Counters)));
+        if (!ps->h_counters) CRAY_CUDA(cudaMallocHost(&ps->h_counters, sizeof(Counters)));
         int sms = 0;
         CRAY_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sc->device));
         int per_sm = 0;
@@ -796,6 +892,7 @@ int ensure_pool(cray_scene* sc, uint32_t capacity) {
         if (const char* e = std::getenv("CRAY_REFILL_LANES")) ps->tune.refill_lanes = std::max(1, std::min(32, std::atoi(e)));
         if (const char* e = std::getenv("CRAY_WAIT_LANES")) ps->tune.wait_lanes = std::max(1, std::min(33, std::atoi(e)));
         if (const char* e = std::getenv("CRAY_BLOCKS_PER_SM")) ps->persistent_blocks = ps->shadow_blocks = ps->f32_blocks = ps->f32_shadow_blocks = (unsigned)(sms * std::max(1, std::atoi(e)));
+        ps->initialised = true;
     }
     if (ps->pool.capacity >= capacity) return CRAY_OK;
     if (ps->slab) { cudaDeviceSynchronize(); cudaFree(ps->slab); ps->slab = nullptr; }  // (re-)allocation is rare: grow only
@@ -830,58 +927,65 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
     Counters* dc = ps->d_counters;
     CRAY_CUDA(cudaMemsetAsync(pool.state, 0, sizeof(uint32_t) * capacity, stream));
     CRAY_CUDA(cudaMemsetAsync(dc, 0, sizeof(Counters), stream));
-    cudaEvent_t e0, e1, gen_done;
-    CRAY_CUDA(cudaEventCreate(&e0)); CRAY_CUDA(cudaEventCreate(&e1));
-    CRAY_CUDA(cudaEventCreateWithFlags(&gen_done, cudaEventDisableTiming));
-    CRAY_CUDA(cudaEventRecord(e0, stream));
-    const unsigned g256 = (capacity + 255) / 256, g128 = (capacity + 127) / 128;
+    struct Events {  // destroyed on every return path
+        cudaEvent_t e0 = nullptr, e1 = nullptr, gen_done = nullptr;
+        ~Events() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (gen_done) cudaEventDestroy(gen_done); }
+    } ev;
+    CRAY_CUDA(cudaEventCreate(&ev.e0)); CRAY_CUDA(cudaEventCreate(&ev.e1));
+    CRAY_CUDA(cudaEventCreateWithFlags(&ev.gen_done, cudaEventDisableTiming));
+    CRAY_CUDA(cudaEventRecord(ev.e0, stream));
+    const unsigned g256 = (capacity + 255) / 256;
+    const unsigned gx = (unsigned)std::min<uint64_t>(kExactBlocks, (capacity + 127) / 128);
     const unsigned gp = ps->persistent_blocks, gs = ps->shadow_blocks;
+    // fast mode: rays that start in a contact shell go to the reference-order kernels (only scenes with marked primitives have any)
+    const bool contact = !job.exact && sc->info.contact_primitives > 0;
     uint64_t iterations = 0, launches = 0, closest = 0;
-    const size_t per_iteration = sizeof(Counters) - offsetof(Counters, n_extend);
     const bool timed = stats != nullptr;
     // The host never waits for traversal or shading: it enqueues the whole iteration, then waits only for the iteration's
     // k_generate (long finished by the time the GPU works through extend / shade / shadow) to learn whether any path is
-    // still alive.  The three launches behind the last, empty generate find empty queues and return at once.
+    // still alive.  The launches behind the last, empty generate find empty queues and return at once.
     constexpr size_t kMarks = 5;  // per iteration: before generate | extend | shade | shadow | after shadow
     for (size_t iter = 0;; ++iter) {
         if (timed) {
             while (ps->timers.size() < kMarks * (iter + 1)) {
-                cudaEvent_t ev;
-                CRAY_CUDA(cudaEventCreate(&ev));
-                ps->timers.push_back(ev);
+                cudaEvent_t t;
+                CRAY_CUDA(cudaEventCreate(&t));
+                ps->timers.push_back(t);
             }
             CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter], stream));
         }
-        CRAY_CUDA(cudaMemsetAsync(&dc->n_extend, 0, per_iteration, stream));
+        k_begin_iteration<<<1, 1, 0, stream>>>(dc);
         k_generate<<<g256, 256, 0, stream>>>(sc->view, pool, job, dc);
         CRAY_CUDA(cudaMemcpyAsync(ps->h_counters, dc, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-        CRAY_CUDA(cudaEventRecord(gen_done, stream));
+        CRAY_CUDA(cudaEventRecord(ev.gen_done, stream));
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 1], stream));
-        if (job.exact) k_extend_exact<<<g128, 128, 0, stream>>>(sc->view, pool, &dc->n_extend);
+        if (job.exact) k_extend_exact<false><<<gx, 128, 0, stream>>>(sc->view, pool, &dc->n_extend);
         else if (job.f32) k_wide_persistent<false, ExtendSource, true><<<ps->f32_blocks, 128, 0, stream>>>(sc->view, ExtendSource{pool}, &dc->n_extend, &dc->extend_cursor, ps->tune);
         else k_wide_persistent<false, ExtendSource><<<gp, 128, 0, stream>>>(sc->view, ExtendSource{pool}, &dc->n_extend, &dc->extend_cursor, ps->tune);
+        if (contact) k_extend_exact<true><<<gx, 128, 0, stream>>>(sc->view, pool, &dc->n_extend_contact);
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 2], stream));
         k_shade<<<(capacity + kShadeThreads - 1) / kShadeThreads, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 3], stream));
-        // at most one shadow ray per shaded vertex; the queue length lives on the device
-        if (job.exact) k_shadow_exact<<<g128, 128, 0, stream>>>(sc->view, pool, &dc->n_shadow);
+        // at most one shadow ray per shaded vertex; the queue lengths live on the device
+        if (job.exact) k_shadow_exact<false><<<gx, 128, 0, stream>>>(sc->view, pool, &dc->n_shadow);
         // (F32 mode traces its shadow rays with the f64 any-hit kernel: measured faster than the f32 one, 20.9 against 24.0 ms per
         // 256-spp dragon frame -- the f32 instantiation's larger shared-memory footprint leaves it less L1 -- and exact at the
         // light's end of the ray.  The f32 any-hit kernel serves cray_trace_any.)
         else k_wide_persistent<true, ShadowSource><<<gs, 128, 0, stream>>>(sc->view, ShadowSource{pool}, &dc->n_shadow, &dc->shadow_cursor, ps->tune);
+        if (contact) k_shadow_exact<true><<<gx, 128, 0, stream>>>(sc->view, pool, &dc->n_shadow_contact);
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 4], stream));
-        launches += 4;
-        CRAY_CUDA(cudaEventSynchronize(gen_done));
-        const uint64_t live = ps->h_counters->n_extend;
+        launches += contact ? 7 : 5;
+        CRAY_CUDA(cudaEventSynchronize(ev.gen_done));
+        const uint64_t live = ps->h_counters->n_extend + ps->h_counters->n_extend_contact;
         if (live == 0) break;
         closest += live;
         iterations += 1;
     }
-    CRAY_CUDA(cudaEventRecord(e1, stream));
-    CRAY_CUDA(cudaEventSynchronize(e1));
+    CRAY_CUDA(cudaEventRecord(ev.e1, stream));
+    CRAY_CUDA(cudaEventSynchronize(ev.e1));
     CRAY_CUDA(cudaGetLastError());
     float ms = 0;
-    CRAY_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    CRAY_CUDA(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
     if (stats) {
         double part[4] = {0.0, 0.0, 0.0, 0.0};  // generate, extend, shade, shadow
         for (size_t i = 0; i < iterations; ++i)
@@ -893,6 +997,8 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
         stats->samples = job.n_total;
         stats->closest_rays = closest;
         stats->shadow_rays = ps->h_counters->shadow_rays;
+        stats->shadow_rays_traced = ps->h_counters->shadow_traced;
+        stats->contact_rays = ps->h_counters->contact_rays;
         stats->nan_samples = ps->h_counters->nan_samples;
         stats->iterations = iterations;
         stats->kernel_launches = launches;
@@ -902,7 +1008,6 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
         stats->shade_ms = part[2];
         stats->shadow_ms = part[3];
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(gen_done);
     return CRAY_OK;
 }
 
@@ -944,6 +1049,7 @@ void cray_pool_release(cray_scene* sc) {
     if (ps->d_film) cudaFree(ps->d_film);
     if (ps->d_film_f32) cudaFree(ps->d_film_f32);
     if (ps->d_trace_counters) cudaFree(ps->d_trace_counters);
+    if (ps->d_trace_list) cudaFree(ps->d_trace_list);
     for (cudaEvent_t ev : ps->timers) cudaEventDestroy(ev);
     delete ps;
     sc->pool = nullptr;
@@ -952,25 +1058,47 @@ void cray_pool_release(cray_scene* sc) {
 
 static int launch_trace(cray_scene* sc, int mode, bool any, const cray_ray* d_rays, uint64_t n, cray_hit* d_hits, cray_surface* d_surf, uint8_t* d_occluded, cudaStream_t stream) {
     CRAY_CUDA(cudaSetDevice(sc->device));
+    if (n > 0xFFFFFFFFull) { set_error("more than 2^32 rays in one call"); return CRAY_E_INVALID; }
+    int rc = ensure_pool(sc, 1);
+    if (rc != CRAY_OK) return rc;
+    auto* ps = static_cast<PoolStorage*>(sc->pool);
+    if (!ps->d_trace_counters) CRAY_CUDA(cudaMalloc(&ps->d_trace_counters, 3 * sizeof(unsigned long long)));
+    unsigned long long* dc = ps->d_trace_counters;  // {rays of the wide launch, its cursor, rays of the reference-order launch}
+    const unsigned exact_blocks = (unsigned)std::min<uint64_t>(kExactBlocks, (n + 127) / 128);
     if (mode == CRAY_TRAVERSE_EXACT) {
-        const uint64_t blocks = (n + 127) / 128;
-        if (any) k_trace_any_exact<<<(unsigned)blocks, 128, 0, stream>>>(sc->view, d_rays, n, d_occluded);
-        else k_trace_closest_exact<<<(unsigned)blocks, 128, 0, stream>>>(sc->view, d_rays, n, d_hits, d_surf);
+        const unsigned long long init[3] = {0ull, 0ull, n};
+        CRAY_CUDA(cudaMemcpyAsync(dc, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+        if (any) k_trace_any_exact<<<exact_blocks, 128, 0, stream>>>(sc->view, d_rays, dc + 2, nullptr, n, d_occluded);
+        else k_trace_closest_exact<<<exact_blocks, 128, 0, stream>>>(sc->view, d_rays, dc + 2, nullptr, n, d_hits, d_surf);
     } else {
-        int rc = ensure_pool(sc, 1);
-        if (rc != CRAY_OK) return rc;
-        auto* ps = static_cast<PoolStorage*>(sc->pool);
-        if (!ps->d_trace_counters) CRAY_CUDA(cudaMalloc(&ps->d_trace_counters, 2 * sizeof(unsigned long long)));
-        const unsigned long long init[2] = {n, 0ull};
-        CRAY_CUDA(cudaMemcpyAsync(ps->d_trace_counters, init, sizeof(init), cudaMemcpyHostToDevice, stream));
         const bool f32 = mode == CRAY_TRAVERSE_F32;
-        const RayArraySource src{d_rays, d_hits, d_surf, d_occluded, f32};
+        // fast / F32 mode on a scene with marked node boxes: the rays that start in a contact shell are traced in reference order
+        const bool split = sc->view.bin_contact != nullptr;
+        uint32_t* list = nullptr;
+        if (split) {
+            if (ps->trace_list_capacity < n) {
+                if (ps->d_trace_list) { CRAY_CUDA(cudaStreamSynchronize(stream)); cudaFree(ps->d_trace_list); ps->d_trace_list = nullptr; ps->trace_list_capacity = 0; }
+                CRAY_CUDA(cudaMalloc(&ps->d_trace_list, n * sizeof(uint32_t)));
+                ps->trace_list_capacity = n;
+            }
+            list = ps->d_trace_list;
+            CRAY_CUDA(cudaMemsetAsync(dc, 0, 3 * sizeof(unsigned long long), stream));
+            k_classify_rays<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(sc->view, d_rays, n, list, dc);
+        } else {
+            const unsigned long long init[3] = {n, 0ull, 0ull};
+            CRAY_CUDA(cudaMemcpyAsync(dc, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+        }
+        const RayArraySource src{d_rays, d_hits, d_surf, d_occluded, f32, list};
         const unsigned resident = f32 ? (any ? ps->f32_shadow_blocks : ps->f32_blocks) : (any ? ps->shadow_blocks : ps->persistent_blocks);
         const unsigned blocks = (unsigned)std::min<uint64_t>(resident, (n + 127) / 128);
-        if (f32 && any) k_wide_persistent<true, RayArraySource, true><<<blocks, 128, 0, stream>>>(sc->view, src, ps->d_trace_counters, ps->d_trace_counters + 1, ps->tune);
-        else if (f32) k_wide_persistent<false, RayArraySource, true><<<blocks, 128, 0, stream>>>(sc->view, src, ps->d_trace_counters, ps->d_trace_counters + 1, ps->tune);
-        else if (any) k_wide_persistent<true, RayArraySource><<<blocks, 128, 0, stream>>>(sc->view, src, ps->d_trace_counters, ps->d_trace_counters + 1, ps->tune);
-        else k_wide_persistent<false, RayArraySource><<<blocks, 128, 0, stream>>>(sc->view, src, ps->d_trace_counters, ps->d_trace_counters + 1, ps->tune);
+        if (f32 && any) k_wide_persistent<true, RayArraySource, true><<<blocks, 128, 0, stream>>>(sc->view, src, dc, dc + 1, ps->tune);
+        else if (f32) k_wide_persistent<false, RayArraySource, true><<<blocks, 128, 0, stream>>>(sc->view, src, dc, dc + 1, ps->tune);
+        else if (any) k_wide_persistent<true, RayArraySource><<<blocks, 128, 0, stream>>>(sc->view, src, dc, dc + 1, ps->tune);
+        else k_wide_persistent<false, RayArraySource><<<blocks, 128, 0, stream>>>(sc->view, src, dc, dc + 1, ps->tune);
+        if (split) {
+            if (any) k_trace_any_exact<<<exact_blocks, 128, 0, stream>>>(sc->view, d_rays, dc + 2, list, n, d_occluded);
+            else k_trace_closest_exact<<<exact_blocks, 128, 0, stream>>>(sc->view, d_rays, dc + 2, list, n, d_hits, d_surf);
+        }
     }
     CRAY_CUDA(cudaGetLastError());
     return CRAY_OK;

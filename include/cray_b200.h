@@ -185,8 +185,12 @@ typedef struct cray_surface {      /* the rest of PrimitiveIntersection  src/int
     double uv[2];
 } cray_surface;
 
-/* EXACT and FAST return the reference's primitive and distance bit for bit (FAST: up to the reference's own false box
- * misses, which only EXACT reproduces).  F32 is the opt-in fast mode of SURVEY 8f n4: the same wide BVH, triangles tested in
+/* EXACT and FAST return the primitive and distance of the reference's algorithm (as restated by the CPU oracle) bit for bit.
+ * EXACT walks the reference's binary tree in the reference's order for every ray.  FAST walks the 8-wide tree, except for rays
+ * whose origin lies in the 1e-9 outer shell of a node box that a planar primitive touches ("planar contact": only there can the
+ * reference's box test, bounds.rs:62-88, cull a subtree a conservative traversal would enter -- the documented bug of
+ * scenes/rounding-error.cry); those rays are traced in reference order too, so the false misses are reproduced.
+ * F32 is the opt-in fast mode of SURVEY 8f n4: the same wide BVH, triangles tested in
  * f32 with the watertight test of Woop, Benthin and Wald (2013) on ray-relative vertices, a ray never re-hits the triangle it
  * leaves, and the hit that was found is re-evaluated in f64 -- so t, u, v equal the parity modes' whenever the same primitive
  * is found, which f32 cannot guarantee for rays grazing an edge.  Spheres and disks stay in f64. */
@@ -210,7 +214,7 @@ int cray_estimate_li(cray_scene*, int mode, uint64_t seed, const uint32_t* x, co
 typedef struct cray_render_stats {
     uint64_t samples;          /* W*H*(sample_end-sample_begin) */
     uint64_t closest_rays;     /* Scene::intersect calls  */
-    uint64_t shadow_rays;      /* Scene::intersects calls */
+    uint64_t shadow_rays;      /* Scene::intersects calls the reference makes: one per path vertex that hits (path_integrator.rs:141) */
     uint64_t nan_samples;      /* samples dropped where the reference would assert (path_integrator.rs:208) */
     uint64_t iterations;       /* wavefront iterations */
     uint64_t kernel_launches;  /* kernels launched by this call */
@@ -219,6 +223,9 @@ typedef struct cray_render_stats {
     double shadow_ms;          /* ... inside the any-hit (shadow) traversal launches */
     double shade_ms;           /* ... inside the shading launches */
     double generate_ms;        /* ... inside the flush / camera-ray launches */
+    uint64_t shadow_rays_traced; /* shadow rays this implementation traced: a vertex whose light sample cannot contribute (black
+                                    contribution, all-specular material) makes the reference's call above but needs no ray here */
+    uint64_t contact_rays;     /* closest + shadow rays of the fast mode that started in a contact shell and took the reference-order traversal */
 } cray_render_stats;
 
 /* Samples [sample_begin, sample_end) of every pixel; film is the SUM over those samples
@@ -252,6 +259,8 @@ typedef struct cray_scene_info {
     uint64_t wide_depth;
     uint32_t width, height, max_depth, num_samples;
     double bvh_build_ms, upload_ms;
+    uint64_t contact_nodes;                 /* binary-BVH node boxes a planar primitive touches (see the traversal modes above) */
+    uint64_t contact_primitives;            /* primitives whose outgoing rays are checked against those boxes */
 } cray_scene_info;
 int cray_scene_get_info(const cray_scene*, cray_scene_info* out);
 

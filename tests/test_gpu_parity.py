@@ -20,7 +20,7 @@ SCENES = {
     # scenes/staircase.cry over the stand-in assets: 26 MTL materials (plastic / conductor / glass), 10 image textures, thin lens
     "staircase_small": (None, [-1.6, -0.1, -2.1], [1.6, 5.6, 3.1]),
     # scenes/cornell.cry over the authored stand-in mesh; planar walls coincide with BVH box faces, so the reference's AABB rule
-    # produces false misses here too (SURVEY A-4b)
+    # produces false misses here too (SURVEY A-4b): both modes reproduce them
     "cornell": (lambda: c.parse_scene(scenes.cornell(width=96, height=96), base_dir=scenes.ASSETS), [-1.1, -0.1, -1.1], [1.1, 2.1, 1.1]),
 }
 FALSE_MISS_SCENES = ("rounding-error", "cornell")
@@ -90,8 +90,6 @@ def test_fixed_ray_batches(name, mode, mode_name):
     hits = 0
     for rays in (b1, b2, b3s, b3c):
         if len(rays):
-            if name in FALSE_MISS_SCENES and mode == c.TRAVERSE_FAST and (rays is b3s or rays is b3c):
-                continue  # covered by test_reference_false_miss_is_reproduced_only_by_exact_mode
             hits += check_closest(gpu, orc, rays, mode)
             assert np.array_equal(gpu.intersects(rays, mode=mode), orc.intersects(rays))
     assert hits > 0
@@ -143,19 +141,29 @@ def test_exact_t_ties_follow_the_reference_visit_order():
 
 
 @pytest.mark.parametrize("name", FALSE_MISS_SCENES)
-def test_reference_false_miss_is_reproduced_only_by_exact_mode(name):
-    """scenes/rounding-error.cry documents a shadow ray that the reference's AABB test wrongly culls (SURVEY A-4b).
-    The exact mode restates that rule and agrees with the oracle on every shadow ray; the wide mode is conservative
-    and reports those rays as occluded.  The mismatch count is reported, not hidden."""
+def test_reference_false_misses_are_reproduced_by_both_modes(name):
+    """scenes/rounding-error.cry documents a shadow ray that the reference's AABB test wrongly culls (SURVEY A-4b): the ray starts
+    within 1e-9 OUTSIDE a node box (a ground point under the ball) and ends inside it.  The exact mode restates that rule for
+    every ray; the fast mode finds the rays that start in such a shell (planar contact analysis at build time + a per-ray test)
+    and traces those in reference order, so both agree with the oracle on every shadow and bounce ray of every pixel -- and the
+    false misses are really there (a conservative traversal would call those rays occluded)."""
     hs, gpu, orc = get_scene(name)
+    assert gpu.info.contact_nodes > 0 and gpu.info.contact_primitives > 0
     xs, ys, ss = pixel_grid(gpu, 1)
-    shadow, _ = orc.bounce_rays(xs, ys, ss)
+    shadow, bounce = orc.bounce_rays(xs, ys, ss)
     ref = orc.intersects(shadow)
-    assert np.array_equal(gpu.intersects(shadow, mode=c.TRAVERSE_EXACT), ref)
-    fast = gpu.intersects(shadow, mode=c.TRAVERSE_FAST)
-    leaks = int((fast & ~ref).sum())
-    assert int((~fast & ref).sum()) == 0          # the wide mode never misses an occluder the reference finds
-    print(f"{name}.cry: {leaks} of {len(shadow)} shadow rays are false misses of the reference's AABB rule")
+    for mode, _ in MODES:
+        assert np.array_equal(gpu.intersects(shadow, mode=mode), ref)
+        check_closest(gpu, orc, bounce, mode)
+    # the false misses are really there: shadow rays the reference calls unoccluded although the same ray with an infinite
+    # max_distance (whose box tests pass: the exit distance is in range) finds an occluder in front of the light
+    probe = shadow.copy()
+    probe["max_distance"] = np.inf
+    far = orc.intersect(probe)
+    occluder_ahead = (far["prim"] != c.CRAY_NO_HIT) & (far["t"] < shadow["max_distance"])
+    leaks = int((occluder_ahead & ~ref).sum())
+    print(f"{name}.cry: {leaks} of {len(shadow)} shadow rays are false misses of the reference's AABB rule (reproduced)")
+    assert leaks > 0
 
 
 @pytest.mark.parametrize("mode,mode_name", MODES)
@@ -210,11 +218,11 @@ def rel_mse(a, b):
 
 def test_cornell_converged_image():
     """BASELINE.json config 2 (cornell.cry, path integrator with NEE) at equal spp, compared the way SURVEY 8(d) states:
-    relMSE(GPU, oracle) <= max(1e-4, 1.5 x relMSE(oracle seed 0, oracle seed 1)) and channel means within 0.5 % for the exact
-    mode.  Per-sample identity is not available on this scene: the floor and walls coincide with BVH box faces, so whether
-    the reference's AABB rule culls a bounce ray hinges on the sign of a ~1e-16 coordinate (SURVEY A-4b), which ulp
-    differences between libm and CUDA sin/cos flip for a few samples.  The wide mode never produces those false misses
-    (it has no light leaks), so it is held to the noise bound only and its deviation is printed."""
+    relMSE(GPU, oracle) <= max(1e-4, 1.5 x relMSE(oracle seed 0, oracle seed 1)) and channel means within 0.5 %, in BOTH modes.
+    Per-sample identity is not available on this scene: the floor and walls coincide with BVH box faces, so whether the
+    reference's AABB rule culls a bounce ray hinges on the sign of a ~1e-16 coordinate (SURVEY A-4b), which ulp differences
+    between libm and CUDA sin/cos flip for a few samples.  The fast mode traces the rays that start in such a contact shell in
+    reference order, so it shows the reference's light leaks like the exact mode does."""
     hs, gpu, orc = get_scene("cornell")
     spp = 64
     ref0, _ = orc.render(gpu.width, gpu.height, seed=0, sample_begin=0, sample_end=spp)
@@ -228,8 +236,7 @@ def test_cornell_converged_image():
         print(f"cornell {mode_name}: relMSE {err:.3e} (seed-to-seed noise {noise:.3e}), channel mean ratios {ratios}")
         assert st.nan_samples == 0
         assert err <= bound, (err, bound)
-        tol = 5e-3 if mode == c.TRAVERSE_EXACT else 2e-2
-        assert all(abs(r - 1.0) <= tol for r in ratios), ratios
+        assert all(abs(r - 1.0) <= 5e-3 for r in ratios), ratios
 
 
 def test_sample_ranges_are_additive_and_deterministic():

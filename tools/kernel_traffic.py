@@ -1,0 +1,57 @@
+#!/usr/bin/env python3
+"""DRAM traffic per launch of the wavefront kernels from one `ncu --set full` report -> profiles/kernel_traffic.json.
+
+usage: kernel_traffic.py report.ncu-rep lib_sha.txt "what was captured" [out.json]
+
+`lib_sha.txt` is the `sha256sum craytracer_b200/libcray_b200.so` written ON THE GPU BOX by tools/final_capture.sh beside the
+report: bench.py reports these figures as `roofline.traffic` only while the library it times has the same hash.  Per kernel
+class the launch with the longest duration is taken (the capture window sits where all path slots are live)."""
+import csv
+import io
+import json
+import subprocess
+import sys
+
+CLASSES = [("extend", "k_wide_persistent<(bool)0, cray::ExtendSource, (bool)0>"), ("shadow", "k_wide_persistent<(bool)1, cray::ShadowSource, (bool)0>"),
+           ("shade", "k_shade"), ("generate", "k_generate"), ("extend_f32", "k_wide_persistent<(bool)0, cray::ExtendSource, (bool)1>")]
+
+
+def main():
+    rep, sha_file, what = sys.argv[1], sys.argv[2], sys.argv[3]
+    out_path = sys.argv[4] if len(sys.argv) > 4 else "profiles/kernel_traffic.json"
+    text = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(text)))
+    hdr, units = rows[0], rows[1]
+    col = {n: hdr.index(n) for n in ("Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum")}
+
+    def to_bytes(v, unit):
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+        return float(v.replace(",", "")) * scale
+
+    def to_ms(v, unit):
+        scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[unit]
+        return float(v.replace(",", "")) * scale
+
+    kernels = {}
+    for key, needle in CLASSES:
+        best = None
+        for r in rows[2:]:
+            if needle not in r[col["Kernel Name"]]:
+                continue
+            ms = to_ms(r[col["gpu__time_duration.sum"]], units[col["gpu__time_duration.sum"]])
+            if best is None or ms > best[0]:
+                rd = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
+                wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
+                best = (ms, rd, wr)
+        if best:
+            kernels[key] = {"dram_bytes_per_launch": best[1] + best[2], "dram_read": best[1], "dram_write": best[2], "launch_ms_under_ncu": best[0]}
+    sha = open(sha_file).read().split()[0]
+    data = {"library_sha256": sha, "source": what, "report": rep, "kernels": kernels}
+    with open(out_path, "w") as f:
+        json.dump(data, f, indent=1)
+        f.write("\n")
+    print(json.dumps(data, indent=1))
+
+
+if __name__ == "__main__":
+    main()
