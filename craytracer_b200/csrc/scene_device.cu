@@ -9,7 +9,7 @@
 
 #include "host_math.hpp"
 #include "sampler.cuh"
-#include "sobol_directions.h"
+#include "../../include/cray_sobol_directions.h"
 
 namespace cray {
 
@@ -163,6 +163,10 @@ int validate(const cray_scene_desc* d) {
     if (d->n_lights == 0) { set_error("No lights in the scene."); return CRAY_E_INVALID; }  // scene_parser.rs:1103
     if (d->n_primitives >= 0xFFFFFFF0ull) { set_error("too many primitives"); return CRAY_E_INVALID; }
     if (d->n_disks > 0x7FFFull) { set_error("more than 32767 disks"); return CRAY_E_UNSUPPORTED; }
+    // The sampler has 256 dimensions (sobol_burley panics beyond them) and a path vertex at bounce b draws dimensions 4 + 8 b .. 11 + 8 b
+    // (path_integrator.rs:25-36): depths beyond 31 have no sample values to draw.  The wavefront's path state also packs the
+    // bounce count into 8 bits.
+    if (d->max_depth > 31) { set_error("max_depth > 31: the Sobol sampler has 256 dimensions, 8 per bounce (the reference panics there)"); return CRAY_E_UNSUPPORTED; }
     if (d->camera.width == 0 || d->camera.height == 0 || d->camera.width > 65535 || d->camera.height > 65535) { set_error("film size out of range"); return CRAY_E_INVALID; }
     for (uint64_t i = 0; i < d->n_primitives; ++i) {
         const cray_primitive_desc& p = d->primitives[i];

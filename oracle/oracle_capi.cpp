@@ -291,6 +291,26 @@ void orc_bounds_union(const double* a6, const double* b6, double* out6) {
     Bounds r = bunion(Bounds{v3(a6), v3(a6 + 3)}, Bounds{v3(b6), v3(b6 + 3)});
     out6[0] = r.min.x; out6[1] = r.min.y; out6[2] = r.min.z; out6[3] = r.max.x; out6[4] = r.max.y; out6[5] = r.max.z;
 }
+// Vector / Point algebra of src/geometry.rs (the operators tests/test_geometry.rs exercises).  op: 0 a + b, 1 a - b, 2 a * s,
+// 3 a / s, 4 cross(a, b), 5 normalized(a); returns dot(a, b) for op 6 and magnitude(a) for op 7 (out untouched).
+double orc_vector_op(int op, const double* a3, const double* b3, double s, double* out3) {
+    const V3 a = v3(a3), b = b3 ? v3(b3) : V3{0.0, 0.0, 0.0};
+    V3 r{0.0, 0.0, 0.0};
+    switch (op) {
+        case 0: r = a + b; break;
+        case 1: r = a - b; break;
+        case 2: r = a * s; break;
+        case 3: r = a / s; break;
+        case 4: r = cross(a, b); break;
+        case 5: r = normalized(a); break;
+        case 6: return dot(a, b);
+        case 7: return magnitude(a);
+        default: break;
+    }
+    out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+    return 0.0;
+}
+
 void orc_reflect(const double* d, const double* n, double* out) {
     V3 r = reflect(v3(d), v3(n));
     out[0] = r.x; out[1] = r.y; out[2] = r.z;

@@ -18,7 +18,7 @@
 // bit-identical sample values; parity with the reference's images is statistical.
 #pragma once
 #include "geometry.hpp"
-#include "sobol_directions.h"
+#include "../include/cray_sobol_directions.h"  // generated constant table (tools/gen_sobol_table.py), shared with the product: data, not code
 
 namespace orc {
 

@@ -48,6 +48,8 @@ def lib():
         L.orc_shape_area.argtypes = [C.c_int, _P]
         L.orc_bounds_intersects.argtypes = [_P, _P, _P]
         L.orc_bounds_union.argtypes = [_P, _P, _P]
+        L.orc_vector_op.restype = C.c_double
+        L.orc_vector_op.argtypes = [C.c_int, _P, _P, C.c_double, _P]
         L.orc_reflect.argtypes = [_P, _P, _P]
         L.orc_refract.argtypes = [_P, _P, C.c_double, C.c_double, C.c_double, _P]
         L.orc_fresnel_dielectric.restype = C.c_double

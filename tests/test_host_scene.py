@@ -124,6 +124,50 @@ def test_wide_bvh_structure(name):
     assert out[0] >= 1 and out[1] >= 1 and out[1] < 30
 
 
+def _contacts(hs):
+    out = (C.c_uint64 * 3)()
+    flags = np.zeros(hs.desc.n_primitives, dtype=np.uint8)
+    assert _abi.lib().cray_debug_find_contacts(hs.desc_ptr, out, flags.ctypes.data) == 0
+    return int(out[0]), int(out[1]), flags
+
+
+def test_planar_contact_analysis_marks_the_false_miss_configurations():
+    """bvh_build.hpp "planar contact": the node boxes a planar primitive touches and the primitives whose outgoing rays can start in
+    the 1e-9 outer shell of such a box -- the only place where the reference's box test (bounds.rs:62-88 with bvh.rs:70,:117) can
+    cull what a conservative traversal enters (SURVEY A-4b)."""
+    # scenes/rounding-error.cry: the ground disk (primitive 0, y = -6e-17 |z|) under the ball's box (min.y = 0 exactly)
+    nodes, prims, flags = _contacts(c.parse_scene(scenes.rounding_error()))
+    assert nodes > 0 and flags.tolist() == [1, 0, 0]
+    # cornell stand-in: floor, ceiling and walls are axis-aligned planes that coincide with faces of the root box and of inner boxes
+    nodes, prims, flags = _contacts(c.parse_scene(scenes.cornell(), base_dir=scenes.ASSETS))
+    assert nodes > 0 and prims >= 8
+    # curved grounds (r = 1e5 spheres) touch boxes at points only: no primitive is marked
+    assert _contacts(c.parse_scene(scenes.materials()))[1] == 0
+    # the dragon stand-in: no planar primitive but the light disk, and no path ray ever leaves an area light
+    c.register_standin_mesh("objs/xyzrgb_dragon.obj", 0, 30001, 0)
+    nodes, prims, flags = _contacts(c.parse_scene(scenes.dragon(), base_dir="/nonexistent"))
+    assert prims == 0 and not flags.any()
+    # a box resting on a ground quad: both ground triangles are marked (they span the box's footprint), the box's own faces are
+    # planar too but only its bottom face lies in a plane that another, thicker node box shares
+    text = """{ camera: Perspective { origin: Point(0, 3, -6), target: Point(0, 0, 0), up: Vector(0, 1, 0), fov: 50, film: { width: 8, height: 8 } },
+      lights: [ Point { origin: Point(0, 5, 0), intensity: Color(10, 10, 10) } ],
+      materials: { m: Matte { reflectance: Color(1, 1, 1), sigma: 0 } },
+      shapes: { g0: Triangle { v0: Point(-4, 0, -4), v1: Point(4, 0, -4), v2: Point(4, 0, 4) }, g1: Triangle { v0: Point(-4, 0, -4), v1: Point(4, 0, 4), v2: Point(-4, 0, 4) },
+                ball: Sphere { origin: Point(0, 1, 0), radius: 1 } },
+      primitives: [ Shape { shape: 'g0', material: 'm' }, Shape { shape: 'g1', material: 'm' }, Shape { shape: 'ball', material: 'm' } ] }"""
+    nodes, prims, flags = _contacts(c.parse_scene(text))
+    assert flags.tolist() == [1, 1, 0] and nodes >= 1
+
+
+def test_scene_description_limits_are_errors():
+    """max_depth beyond the sampler's 256 dimensions (8 per bounce) is refused before any device is touched."""
+    hs = c.parse_scene(scenes.simple(width=16, height=16).replace("num_samples:", "max_depth: 32, num_samples:", 1))
+    assert hs.desc.max_depth == 32
+    with pytest.raises(c.CrayError) as e:
+        c.Scene(hs)
+    assert e.value.code == _abi.CRAY_E_UNSUPPORTED and "max_depth" in e.value.message
+
+
 def test_bvh_degenerate_input_is_an_error_not_a_crash():
     # > 4 primitives sharing one centroid: the reference asserts (bvh.rs:327-328); the ABI reports CRAY_E_BVH
     prims = ", ".join("Shape { shape: 's', material: 'm' }" for _ in range(6))

@@ -1,5 +1,5 @@
 """Pins the CPU oracle against every known-answer test the reference holds for the hot path
-(tests/test_shape.rs, test_bvh.rs, test_bounds.rs, test_bxdf.rs, test_transformation.rs, test_color.rs, test_util.rs),
+(tests/test_geometry.rs, test_shape.rs, test_bvh.rs, test_bounds.rs, test_bxdf.rs, test_transformation.rs, test_color.rs, test_util.rs),
 restated one-to-one, plus independent pins for the third-party sampler arithmetic (SipHash, Sobol)."""
 import ctypes as C
 import itertools
@@ -33,6 +33,45 @@ def shape_intersect(orc, kind, params, origin, direction, max_distance=np.inf):
     out = np.zeros(9)
     hit = orc.orc_shape_intersect(kind, p.ctypes.data, r.ctypes.data, out.ctypes.data)
     return hit, out[0:3], out[3:6], out[6:8], out[8]
+
+
+# ---- tests/test_geometry.rs (vector :9-105, point :113-153) --------------------------------------------------------------
+
+def vec_op(orc, op, a, b=None, s=0.0):
+    out = np.zeros(3)
+    av = o.f64(*a)
+    bv = o.f64(*b) if b is not None else None
+    val = orc.orc_vector_op(op, av.ctypes.data, bv.ctypes.data if b is not None else None, s, out.ctypes.data)
+    return val if op >= 6 else tuple(out)
+
+
+ADD, SUB, MUL, DIV, CROSS, NORMALIZED, DOT, MAGNITUDE = range(8)
+X, Y, Z = (1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0)
+
+
+def test_vector_normalized_magnitude_dot(orc):  # test_geometry.rs:9-26
+    assert vec_op(orc, NORMALIZED, (1, 2, 2)) == (1.0 / 3.0, 2.0 / 3.0, 2.0 / 3.0)
+    assert vec_op(orc, MAGNITUDE, (1, 2, 2)) == 3.0
+    assert vec_op(orc, DOT, (1, 2, 3), (-2, 2, 0.5)) == 3.5
+
+
+def test_vector_cross(orc):  # :28-42
+    assert vec_op(orc, CROSS, X, Y) == Z and vec_op(orc, CROSS, Y, Z) == X and vec_op(orc, CROSS, Z, X) == Y
+    a = (1, 1, 0)
+    assert vec_op(orc, CROSS, a, a) == (0, 0, 0)      # cross product with itself is the null vector
+    assert vec_op(orc, CROSS, a, X) == (0, 0, -1)
+    assert vec_op(orc, CROSS, a, Y) == (0, 0, 1)
+    assert vec_op(orc, CROSS, a, Z) == (1, -1, 0)
+
+
+def test_vector_and_point_arithmetic(orc):  # :44-105 and :113-153 (Vector, Point and Normal share the component-wise operators)
+    a, ones = (1, 2, 3), (1, 1, 1)
+    assert a == (1, 2, 3) and a != (2, 1, 3)                              # equal (:44-50, :113-119)
+    assert vec_op(orc, ADD, a, ones) == (2, 3, 4)                          # add / add_assign (:52-64, :121-133)
+    assert vec_op(orc, SUB, a, ones) == (0, 1, 2)                          # sub / sub_assign / sub_vector (:66-78, :135-153)
+    assert vec_op(orc, MUL, a, s=2.0) == (2, 4, 6)                         # mul / mul_assign (:80-92)
+    assert vec_op(orc, DIV, a, s=2.0) == (0.5, 1.0, 1.5)                   # div (:94-98)
+    assert vec_op(orc, MUL, a, s=0.5) == (0.5, 1.0, 1.5)                   # div_assign is written `a *= 0.5` (:100-105)
 
 
 # ---- tests/test_shape.rs ------------------------------------------------------------------------------------------
