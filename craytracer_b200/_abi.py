@@ -15,6 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libcray_b200.so")
 CRAY_OK = 0
 CRAY_E_INVALID, CRAY_E_CUDA, CRAY_E_PARSE, CRAY_E_IO, CRAY_E_BVH, CRAY_E_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 CRAY_NO_HIT = 0xFFFFFFFF
+CRAY_TEX_CONSTANT, CRAY_TEX_CHECKERBOARD, CRAY_TEX_IMAGE = 0, 1, 2
+CRAY_MAT_MATTE, CRAY_MAT_GLASS, CRAY_MAT_PLASTIC, CRAY_MAT_METAL = 0, 1, 2, 3
 SHAPE_SPHERE, SHAPE_TRIANGLE, SHAPE_DISK = 0, 1, 2
 TEX_CONSTANT, TEX_CHECKERBOARD, TEX_IMAGE = 0, 1, 2
 MAT_MATTE, MAT_GLASS, MAT_PLASTIC, MAT_METAL = 0, 1, 2, 3
@@ -133,6 +135,7 @@ SIGNATURES = {
 EXTRA_SIGNATURES = {
     "cray_set_image_decoder": (None, [IMAGE_DECODER]),
     "cray_clear_standin_meshes": (None, []),
+    "cray_debug_decode_image": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(_P)]),
     "cray_debug_transformation": (None, [C.c_int, _P, _P, _P]),
     "cray_debug_matrix_inverse": (C.c_int, [_P, _P]),
     "cray_debug_camera_matrices": (None, [C.POINTER(CameraDesc), _P]),

@@ -9,6 +9,7 @@
 #include "../../include/cray_b200.h"
 #include "cry_parser.hpp"
 #include "host_scene.hpp"
+#include "image_decode.hpp"
 #include "host_math.hpp"
 #include "bvh_build.hpp"
 
@@ -152,6 +153,18 @@ uint64_t cray_host_scene_num_warnings(const cray_host_scene* hs) { return hs ? h
 const char* cray_host_scene_warning(const cray_host_scene* hs, uint64_t i) { return hs && i < hs->scene->warnings.size() ? hs->scene->warnings[i].c_str() : ""; }
 
 void cray_set_image_decoder(cray::image_decoder_fn fn) { cray::set_image_decoder(fn); }
+
+// The built-in texture decoder on its own (tests/test_image_decode.py): RGB8 rows in a buffer to release with cray_free.
+int cray_debug_decode_image(const uint8_t* bytes, uint64_t n, uint32_t* width, uint32_t* height, uint8_t** rgb) {
+    std::vector<uint8_t> out;
+    std::string why;
+    if (!bytes || !width || !height || !rgb) { cray::set_error("null argument"); return CRAY_E_INVALID; }
+    if (!cray::decode_image(bytes, (size_t)n, *width, *height, out, why)) { cray::set_error(why); return CRAY_E_UNSUPPORTED; }
+    *rgb = static_cast<uint8_t*>(std::malloc(out.size() ? out.size() : 1));
+    if (!*rgb) { cray::set_error("out of memory"); return CRAY_E_INVALID; }
+    std::memcpy(*rgb, out.data(), out.size());
+    return CRAY_OK;
+}
 void cray_register_standin_mesh(const char* file_name, int kind, uint64_t triangles, uint64_t seed) { cray::register_standin_mesh(file_name, kind, triangles, seed); }
 void cray_clear_standin_meshes(void) { cray::clear_standin_meshes(); }
 

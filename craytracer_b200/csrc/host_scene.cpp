@@ -6,12 +6,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iterator>
 #include <functional>
 #include <map>
 #include <sstream>
 #include <unordered_map>
 
 #include "cray_math.cuh"
+#include "image_decode.hpp"
 
 namespace cray {
 
@@ -180,13 +182,20 @@ int load_image(HostScene& hs, const std::string& path) {  // load_texture obj.rs
     bool ok = false;
     if (path.size() > 4 && path.substr(path.size() - 4) == ".ppm") ok = load_ppm(path, w, h, rgb);
     if (!ok) {
-        std::ifstream probe(path, std::ios::binary);
-        if (!probe) throw IoError{"Could not find texture file \"" + path + "\""};
-        if (!g_decoder) throw UnsupportedError{"no image decoder registered for texture \"" + path + "\" (only binary PPM is built in)"};
-        uint8_t* buf = nullptr;
-        if (g_decoder(path.c_str(), &w, &h, &buf) != 0 || !buf) throw IoError{"could not decode texture \"" + path + "\""};
-        rgb.assign(buf, buf + (size_t)w * h * 3);
-        std::free(buf);
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw IoError{"Could not find texture file \"" + path + "\""};
+        const std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        std::string why;
+        ok = decode_image(bytes.data(), bytes.size(), w, h, rgb, why);  // built in: JPEG, PNG (image_decode.cpp)
+        if (!ok && g_decoder) {  // any other format: the host's hook, if it registered one
+            uint8_t* buf = nullptr;
+            if (g_decoder(path.c_str(), &w, &h, &buf) == 0 && buf) {
+                rgb.assign(buf, buf + (size_t)w * h * 3);
+                std::free(buf);
+                ok = true;
+            }
+        }
+        if (!ok) throw IoError{"could not decode texture \"" + path + "\": " + why};
     }
     hs.images.push_back({w, h, nullptr});
     hs.image_data.push_back(std::move(rgb));

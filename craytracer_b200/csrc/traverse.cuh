@@ -214,7 +214,7 @@ __device__ __forceinline__ void warp_begin_ray(WarpShared& ws, unsigned lane, V3
 // One interior node for one ray: pops the nearest pending child of the node group `ng`, tests its 8 quantised child boxes,
 // leaves the interior children hit in `ng` (octant ordered) and queues the primitives whose box was hit.
 template <class WS>
-__device__ __forceinline__ void node_step(const SceneView& s, WS& ws, unsigned lane, const WideRay& r, uint2& ng, uint2* stack, int& sp) {
+__device__ __forceinline__ uint32_t node_step(const SceneView& s, WS& ws, unsigned lane, const WideRay& r, uint2& ng, uint2* stack, int& sp) {
     const uint32_t bit = 31u - __clz(ng.y);
     ng.y &= ~(1u << bit);
     const uint32_t slot = (bit - 24u) ^ r.octinv;
@@ -283,6 +283,7 @@ __device__ __forceinline__ void node_step(const SceneView& s, WS& ws, unsigned l
     ng = make_uint2((uint32_t)n1.x, (ih << 24) | imask);
     // primitives: one per leaf slot, contiguous from prim_base in ascending slot order
     uint32_t lh = hits & leafmask;
+    const uint32_t outcome = ih | (lh << 8);   // (work counters of the stats build)
     if (lh) {
         const uint32_t n = __popc(lh);
         uint32_t pos = atomicAdd(&ws.tail, n);
@@ -296,6 +297,7 @@ __device__ __forceinline__ void node_step(const SceneView& s, WS& ws, unsigned l
             pos += 1u;
         } while (lh);
     }
+    return outcome;
 }
 
 // Runs the first min(count, 32) queued tests, one per lane (closest-hit flavour).  The lanes testing primitives for the same

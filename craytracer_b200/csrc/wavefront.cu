@@ -209,11 +209,13 @@ enum : int { LANE_IDLE = 0, LANE_LIVE = 1, LANE_DRAIN = 2 };
 // Tuning build (make VARIANT=stats EXTRA=-DCRAY_WIDE_STATS=1): work counters of the traversal kernels, read with
 // cray_debug_wide_stats.  [0] rays  [1] warp iterations  [2] node steps (lanes)  [3] node phases (warps)
 // [4] primitive tests (lanes)  [5] primitive rounds (warps)  [6] refills (warps)  [7] idle-lane iterations
+// [8] node steps that hit nothing  [9] interior children hit  [10] node steps that queued no primitive  [11] node steps taken
+// while the lane's ray already had a hit (closest) 
 #ifndef CRAY_WIDE_STATS
 #define CRAY_WIDE_STATS 0
 #endif
 #if CRAY_WIDE_STATS
-__device__ unsigned long long g_wide_stats[2][8];
+__device__ unsigned long long g_wide_stats[2][12];
 #define WIDE_STAT(k, v) stat[k] += (unsigned long long)(v)
 #else
 #define WIDE_STAT(k, v)
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(128, F32 ? kWideMinBlocksF32 : (ANY ? kWideMin
     __syncwarp();
     uint32_t head = 0;  // queue entries consumed so far (warp-uniform)
 #if CRAY_WIDE_STATS
-    unsigned long long stat[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long stat[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
     WideRay r;
     uint2 ng = make_uint2(0u, 0u);
@@ -277,7 +279,21 @@ __global__ void __launch_bounds__(128, F32 ? kWideMinBlocksF32 : (ANY ? kWideMin
         if (state == LANE_LIVE) {
             if (!(ng.y & 0xFF000000u) && sp > 0) ng = stack[--sp];
             stepping = (ng.y & 0xFF000000u) != 0u;
-            if (stepping) node_step(s, ws, lane, r, ng, stack, sp);
+            uint32_t outcome = 0xFFFFFFFFu;
+            if (stepping) outcome = node_step(s, ws, lane, r, ng, stack, sp);
+#if CRAY_WIDE_STATS
+            {
+                const unsigned m = __activemask();
+                WIDE_STAT(8, __popc(__ballot_sync(m, outcome == 0u)));
+                WIDE_STAT(10, __popc(__ballot_sync(m, stepping && (outcome >> 8) == 0u)));
+                WIDE_STAT(11, __popc(__ballot_sync(m, stepping && ws.best[lane] != (ANY ? 0u : CRAY_NO_HIT))));
+                unsigned ihs = stepping ? __popc(outcome & 0xFFu) : 0u;
+                for (int o = 16; o; o >>= 1) ihs += __shfl_xor_sync(m, ihs, o);
+                WIDE_STAT(9, ihs);
+            }
+#else
+            (void)outcome;
+#endif
             // a node group with nothing left to visit is replaced from the stack right away: the (local-memory) load has the
             // rest of the iteration to arrive instead of stalling the next node step
             if (!(ng.y & 0xFF000000u) && sp > 0) ng = stack[--sp];
@@ -328,7 +344,7 @@ __global__ void __launch_bounds__(128, F32 ? kWideMinBlocksF32 : (ANY ? kWideMin
     }
 #if CRAY_WIDE_STATS
     if (lane == 0)
-        for (int k = 0; k < 8; ++k) atomicAdd(&g_wide_stats[ANY ? 1 : 0][k], stat[k]);
+        for (int k = 0; k < 12; ++k) atomicAdd(&g_wide_stats[ANY ? 1 : 0][k], stat[k]);
 #endif
 }
 
@@ -1025,10 +1041,10 @@ using namespace cray;
 
 extern "C" {
 
-// Tuning builds only (CRAY_WIDE_STATS): copies and clears the traversal work counters, [0..7] closest-hit, [8..15] any-hit.
+// Tuning builds only (CRAY_WIDE_STATS): copies and clears the traversal work counters, [0..11] closest-hit, [12..23] any-hit.
 int cray_debug_wide_stats(unsigned long long* out16) {
 #if CRAY_WIDE_STATS
-    unsigned long long zero[16] = {};
+    unsigned long long zero[24] = {};
     CRAY_CUDA(cudaDeviceSynchronize());
     CRAY_CUDA(cudaMemcpyFromSymbol(out16, g_wide_stats, sizeof(zero)));
     CRAY_CUDA(cudaMemcpyToSymbol(g_wide_stats, zero, sizeof(zero)));

@@ -235,6 +235,98 @@ def rounding_error(num_samples=10, width=400, height=400):
 }}"""
 
 
+# ---- objs/staircase: the material library and texture set of the reference's staircase scene -------------------------
+#
+# The reference ships objs/staircase/staircase.mtl (26 materials, Blender export) and ten JPEG textures (27.6 M texels, 83 MB as
+# RGB8) but not the mesh.  The material table below restates the MTL's values in file order; the textures cannot be redistributed,
+# so `write_staircase_assets` synthesises images with the reference files' names, dimensions and JPEG encodings (baseline or
+# progressive, chroma subsampling, restart interval).  tests/test_host_scene.py checks the generated library against the
+# reference's own file when /root/reference is present.
+#            name                        Ns      Kd                   Ks                 Ni   d    illum  map_Kd
+STAIRCASE_MATERIALS = [
+    ("Black",                    250.0, (0.8, 0.8, 0.8),     (0.0, 0.0, 0.0),   1.0, 1.0, 2, None),
+    ("Black.002",                250.0, (0.6, 0.6, 0.6),     (0.0, 0.0, 0.0),   1.0, 1.0, 2, None),
+    ("Brass",                    250.0, (0.9, 0.8, 0.5),     (3.0, 2.0, 1.0),   1.0, 1.0, 4, None),
+    ("Brushed_Aluminium",        250.0, (0.9, 0.7, 0.4),     (4.0, 3.0, 2.0),   1.0, 1.0, 4, "BrushedAluminium.jpg"),
+    ("Brushed_Stainless_Steel",  250.0, (0.9, 0.7, 0.4),     (4.0, 3.0, 2.0),   1.0, 1.0, 4, None),
+    ("Candles",                  250.0, (0.9, 0.8, 0.5),     (0.0, 0.0, 0.0),   1.0, 1.0, 2, None),
+    ("Chair_Seat",                 0.0, (0.09, 0.02, 0.08),  (0.0, 0.0, 0.0),   1.0, 1.0, 2, "Fabric.jpg"),
+    ("Emission",                 250.0, (0.8, 0.8, 0.8),     (0.0, 0.0, 0.0),   1.0, 1.0, 2, None),
+    ("Glass",                    250.0, (1.0, 1.0, 1.0),     (1.0, 1.0, 1.0),   1.1, 0.1, 2, None),
+    ("Gold",                     250.0, (0.2, 0.4, 1.4),     (3.4, 2.3, 1.8),   1.0, 1.0, 4, None),
+    ("Lampshade_material",       250.0, (0.8, 0.65, 0.45),   (0.0, 0.0, 0.0),   1.0, 1.0, 2, None),
+    ("Material.001",               0.0, (0.02, 0.05, 0.03),  (0.0, 0.0, 0.0),   1.0, 1.0, 2, None),
+    ("Paint_-_Magnolia_Matt",    250.0, (0.8, 0.8, 0.8),     (0.0, 0.0, 0.0),   1.0, 1.0, 2, None),
+    ("Paint_-_White_Gloss",      250.0, (0.8, 0.8, 0.8),     (0.0, 0.0, 0.0),   1.0, 1.0, 2, None),
+    ("Paint_-_White_Matt",       250.0, (0.8, 0.8, 0.8),     (0.0, 0.0, 0.0),   1.0, 1.0, 2, None),
+    ("Painting",                 250.0, (0.8, 0.8, 0.8),     (0.0, 0.0, 0.0),   1.0, 1.0, 2, "Painting3.jpg"),
+    ("Painting_01",              250.0, (0.8, 0.8, 0.8),     (0.0, 0.0, 0.0),   1.0, 1.0, 2, "Painting1.jpg"),
+    ("Painting_02",              250.0, (0.8, 0.8, 0.8),     (0.0, 0.0, 0.0),   1.0, 1.0, 2, "Painting2.jpg"),
+    ("Wallpaper",                250.0, (0.9, 0.8, 0.6),     (0.3, 0.3, 0.3),   1.0, 1.0, 2, "Wallpaper.jpg"),
+    ("White.001",                250.0, (1.0, 1.0, 1.0),     (0.0, 0.0, 0.0),   1.0, 1.0, 2, None),
+    ("White_Plastic",            250.0, (0.8, 0.8, 0.8),     (0.0, 0.0, 0.0),   1.0, 1.0, 2, None),
+    ("Wood_-_Chair",             250.0, (0.8, 0.3, 0.1),     (1.0, 1.0, 1.0),   1.0, 1.0, 2, "WoodChair.jpg"),
+    ("Wood_-_Floor",            1000.0, (0.8, 0.3, 0.1),     (1.0, 1.0, 1.0),   1.0, 1.0, 2, "WoodFloor.jpg"),
+    ("Wood_-_Lamp",              250.0, (0.6, 0.4, 0.1),     (1.0, 1.0, 1.0),   1.0, 1.0, 2, "Wood.jpg"),
+    ("Wood_-_Stairs",           1000.0, (0.8, 0.3, 0.1),     (1.0, 1.0, 1.0),   1.0, 1.0, 2, "WoodPanel.jpg"),
+    ("copper.001",               250.0, (0.9, 0.9, 0.1),     (0.1, 0.1, 0.1),   1.0, 1.0, 4, None),
+]
+# file name -> (width, height, chroma subsampling as PIL names it (0 = 4:4:4, 2 = 4:2:0), progressive, restart interval in MCUs)
+STAIRCASE_TEXTURES = {
+    "BrushedAluminium.jpg": (3500, 2625, 0, False, 438),
+    "Fabric.jpg": (2048, 1382, 2, False, 0),
+    "Painting1.jpg": (1024, 1024, 2, False, 0),
+    "Painting2.jpg": (1440, 1440, 2, False, 0),
+    "Painting3.jpg": (1920, 1920, 2, False, 0),
+    "Wallpaper.jpg": (512, 512, 2, False, 0),
+    "Wood.jpg": (1024, 689, 0, False, 128),
+    "WoodChair.jpg": (3000, 2139, 0, False, 375),
+    "WoodFloor.jpg": (960, 870, 2, False, 0),
+    "WoodPanel.jpg": (726, 821, 0, True, 0),
+}
+STAIRCASE_FULL = os.path.join(ASSETS, "_generated", "staircase_full")   # git-ignored; written on first use
+
+
+def staircase_mtl_text():
+    lines = ["# objs/staircase/staircase.mtl: the reference's material library, restated from craytracer_b200/scenes.py", ""]
+    for name, ns, kd, ks, ni, d, illum, tex in STAIRCASE_MATERIALS:
+        lines += [f"newmtl {name}", f"Ns {ns}", "Ka 1.0 1.0 1.0", "Kd {} {} {}".format(*kd), "Ks {} {} {}".format(*ks), "Ke 0.0 0.0 0.0", f"Ni {ni}", f"d {d}"]
+        if tex:
+            lines.append(f"map_Kd textures/{tex}")
+        lines += [f"illum {illum}", ""]
+    return "\n".join(lines)
+
+
+def write_staircase_assets(base_dir=STAIRCASE_FULL):
+    """Writes <base_dir>/objs/staircase/staircase.mtl and its ten JPEG textures (synthetic content, the reference's dimensions and
+    encodings) unless they are already there; returns base_dir, to be passed as the scene's base directory.  Needs PIL to encode."""
+    import numpy as np
+    from PIL import Image
+    root = os.path.join(base_dir, "objs", "staircase")
+    os.makedirs(os.path.join(root, "textures"), exist_ok=True)
+    mtl = os.path.join(root, "staircase.mtl")
+    if not os.path.exists(mtl) or open(mtl).read() != staircase_mtl_text():
+        with open(mtl, "w") as f:
+            f.write(staircase_mtl_text())
+    for k, (name, (w, h, subsampling, progressive, restart)) in enumerate(sorted(STAIRCASE_TEXTURES.items())):
+        path = os.path.join(root, "textures", name)
+        if os.path.exists(path):
+            continue
+        ys, xs = np.mgrid[0:h, 0:w].astype(np.float32)
+        rng = np.random.default_rng(1000 + k)
+        f1, f2, ph = rng.uniform(0.004, 0.03, 2), rng.uniform(0.05, 0.2, 2), rng.uniform(0, 6.28, 3)
+        grain = np.sin(xs * f1[0] + 6.0 * np.sin(ys * f1[1] + ph[0]) + ph[1]) * 0.5 + 0.5          # wood-grain-like bands
+        weave = (np.sin(xs * f2[0]) * np.sin(ys * f2[1] + ph[2])) * 0.5 + 0.5                        # fine weave
+        base = rng.uniform(0.25, 0.9, 3).astype(np.float32)
+        img = np.stack([(0.55 * grain + 0.25 * weave + 0.2) * base[c] for c in range(3)], axis=-1)
+        img = np.clip(img * 255.0 + rng.normal(0.0, 2.0, img.shape).astype(np.float32), 0, 255).astype(np.uint8)
+        tmp = path + ".tmp"
+        Image.fromarray(img).save(tmp, "JPEG", quality=88, subsampling=subsampling, progressive=progressive, optimize=progressive,
+                                  **({"restart_marker_blocks": restart} if restart else {}))
+        os.replace(tmp, path)
+    return base_dir
+
+
 def register_standins(dragon_triangles=DRAGON_TRIANGLES, interior_triangles=1_500_000):
     """Stand-ins for the meshes the reference does not ship; real files win when present under the base directory."""
     register_standin_mesh("objs/xyzrgb_dragon.obj", 0, dragon_triangles, 0)

@@ -302,3 +302,51 @@ def test_ctypes_constants_match_the_header():
     modes = re.search(r"enum\s*\{\s*CRAY_TRAVERSE_EXACT\s*=\s*(\d+),\s*CRAY_TRAVERSE_FAST\s*=\s*(\d+),\s*CRAY_TRAVERSE_F32\s*=\s*(\d+)\s*\}", header)
     assert tuple(int(g) for g in modes.groups()) == (_abi.TRAVERSE_EXACT, _abi.TRAVERSE_FAST, _abi.TRAVERSE_F32)
     assert int(defines["CRAY_E_PARSE"]) == _abi.CRAY_E_PARSE
+
+
+def _staircase_library(base_dir):
+    c.register_standin_mesh("objs/staircase/staircase.obj", 1, 3000, 0)
+    hs = c.parse_scene(scenes.staircase(width=72, height=128), base_dir=base_dir)
+    d = hs.desc
+    mats = bytes(C.string_at(d.materials, C.sizeof(_abi.MaterialDesc) * d.n_materials))
+    dims = [(d.images[i].width, d.images[i].height) for i in range(d.n_images)]
+    return hs, mats, dims
+
+
+def test_staircase_material_library_and_jpeg_textures_load_in_the_compiled_host():
+    """objs/staircase/staircase.mtl as the reference ships it (26 materials: illum 4 -> Metal, d < 1 -> Glass, otherwise Plastic
+    with map_Kd, src/obj.rs:61-105) with ten JPEG textures of the reference's sizes, decoded by the C++ host itself."""
+    base = scenes.write_staircase_assets()
+    hs, mats, dims = _staircase_library(base)
+    d = hs.desc
+    assert d.n_materials == 1 + len(scenes.STAIRCASE_MATERIALS)  # the scene's `default` + the library
+    assert sorted(dims) == sorted((w, h) for (w, h, *_rest) in scenes.STAIRCASE_TEXTURES.values())
+    assert sum(w * h for w, h in dims) == 27_642_338
+    kinds = [d.materials[1 + i].kind for i in range(len(scenes.STAIRCASE_MATERIALS))]
+    for (name, _ns, _kd, _ks, _ni, dissolve, illum, tex), kind, i in zip(scenes.STAIRCASE_MATERIALS, kinds, range(len(kinds))):
+        want = _abi.CRAY_MAT_METAL if illum == 4 else (_abi.CRAY_MAT_GLASS if dissolve < 1.0 else _abi.CRAY_MAT_PLASTIC)
+        assert kind == want, name
+        if tex and kind == _abi.CRAY_MAT_PLASTIC:
+            t0 = d.materials[1 + i].t0
+            assert t0.kind == _abi.CRAY_TEX_IMAGE and (d.images[t0.image].width, d.images[t0.image].height) == scenes.STAIRCASE_TEXTURES[tex][:2], name
+    # a texel of a decoded texture is what PIL reads from the same file
+    Image = pytest.importorskip("PIL.Image")
+    tex_dir = os.path.join(base, "objs", "staircase", "textures")
+    by_dims = {}
+    for n in os.listdir(tex_dir):
+        im = np.asarray(Image.open(os.path.join(tex_dir, n)).convert("RGB"))
+        by_dims[(im.shape[1], im.shape[0])] = im
+    for i in range(d.n_images):
+        w, h = d.images[i].width, d.images[i].height
+        got = np.ctypeslib.as_array(d.images[i].rgb, shape=(h, w, 3))
+        assert np.array_equal(got, by_dims[(w, h)])
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFERENCE, "objs", "staircase", "staircase.mtl")), reason="reference assets not mounted")
+def test_generated_staircase_library_equals_the_reference_file():
+    """The material table of craytracer_b200/scenes.py against the reference's own staircase.mtl + JPEGs: same materials byte for
+    byte (kinds, colours, roughness, eta, texture bindings) and the same texture dimensions."""
+    _, ref_mats, ref_dims = _staircase_library(REFERENCE)
+    _, gen_mats, gen_dims = _staircase_library(scenes.write_staircase_assets())
+    assert ref_dims == gen_dims
+    assert ref_mats == gen_mats
