@@ -11,10 +11,23 @@ struct Hit {
     uint32_t slot;    // index into the leaf-ordered LeafPrim array that was traversed, CRAY_NO_HIT = miss
 };
 
+#ifndef CRAY_PRIM_NOALLOC
+#define CRAY_PRIM_NOALLOC 1   // 1: intersection records bypass L1 allocation (each is read about once; L1 is kept for the nodes)
+#endif
+__device__ __forceinline__ double2 ldg_record(const double2* p) {
+#if CRAY_PRIM_NOALLOC
+    double2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 // Five 16-byte read-only loads straight into registers (no round trip through a local-memory copy of the record).
 __device__ __forceinline__ LeafPrim load_leaf_prim(const LeafPrim* p) {
     const double2* src = reinterpret_cast<const double2*>(p);
-    const double2 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), e = __ldg(src + 3), f = __ldg(src + 4);
+    const double2 a = ldg_record(src), b = ldg_record(src + 1), c = ldg_record(src + 2), e = ldg_record(src + 3), f = ldg_record(src + 4);
     LeafPrim r;
     r.d[0] = a.x; r.d[1] = a.y; r.d[2] = b.x; r.d[3] = b.y; r.d[4] = c.x; r.d[5] = c.y; r.d[6] = e.x; r.d[7] = e.y; r.d[8] = f.x;
     r.prim = (uint32_t)__double2loint(f.y);
@@ -143,6 +156,18 @@ __device__ __noinline__ int analytic_candidate(const SceneView& s, const LeafPri
     return 0;
 }
 
+#ifndef CRAY_PRIM_NOCOPY
+#define CRAY_PRIM_NOCOPY 0   // 1: the out-of-line analytic tests read the record themselves (no local-memory copy of every tested record)
+#endif
+__device__ __noinline__ int analytic_candidate_at(const SceneView& s, const LeafPrim* record, V3 o, V3 dir, double& ray_max, bool have_hit) {
+    const LeafPrim lp = load_leaf_prim(record);
+    return analytic_candidate(s, lp, o, dir, ray_max, have_hit);
+}
+__device__ __noinline__ bool analytic_any_at(const SceneView& s, const LeafPrim* record, V3 o, V3 dir, double ray_max) {
+    const LeafPrim lp = load_leaf_prim(record);
+    return leaf_prim_any(s, lp, o, dir, ray_max);
+}
+
 // ... and the any-hit test of a sphere or disk, out of line for the same reason (F32 mode)
 __device__ __noinline__ bool analytic_any(const SceneView& s, const LeafPrim& lp, V3 o, V3 dir, double ray_max) {
     return leaf_prim_any(s, lp, o, dir, ray_max);
@@ -173,7 +198,8 @@ __device__ __forceinline__ bool triangle_eval_unchecked(const double* d9, V3 o, 
 // Wide-BVH closest-hit flavour.  0: rejected; 1: accepted (ray_max shrinks); 2: exact tie -- the strict `<` of
 // ray.rs:26 rejects it against the current ray_max, but its distance is bit-equal to it, so the reference keeps
 // whichever of the two primitives its own traversal reaches first.
-__device__ __forceinline__ int leaf_prim_candidate(const SceneView& s, const LeafPrim& lp, V3 o, V3 dir, double& ray_max, bool have_hit, double& u, double& v) {
+__device__ __forceinline__ int leaf_prim_candidate(const SceneView& s, const LeafPrim& lp, V3 o, V3 dir, double& ray_max, bool have_hit, double& u, double& v,
+                                                   const LeafPrim* record = nullptr) {
     const uint32_t kind = lp.kind & 0xFFu;
     if (kind == PRIM_TRIANGLE) {
         double t, tu, tv;
@@ -182,7 +208,12 @@ __device__ __forceinline__ int leaf_prim_candidate(const SceneView& s, const Lea
         if (have_hit && t == ray_max) { u = tu; v = tv; return 2; }
         return 0;
     }
+#if CRAY_PRIM_NOCOPY
+    return analytic_candidate_at(s, record, o, dir, ray_max, have_hit);
+#else
+    (void)record;
     return analytic_candidate(s, lp, o, dir, ray_max, have_hit);
+#endif
 }
 
 // The rest of PrimitiveIntersection (location, normal, uv) for an accepted hit at distance t.  `want_uv` = false skips the

@@ -16,7 +16,11 @@
 namespace cray {
 
 constexpr int kExactStack = 96;
-constexpr int kWideStack = kWideStackLimit;   // node groups: at most one entry per level, the builder rejects deeper trees
+#ifndef CRAY_NODE_PAIR
+#define CRAY_NODE_PAIR 0   // 1: two nodes per lane and step (node_step_pair)
+#endif
+// node groups: at most one entry per level, the builder rejects deeper trees; paired steps may hold kWideStackLimit more
+constexpr int kWideStack = CRAY_NODE_PAIR ? 2 * kWideStackLimit : kWideStackLimit;
 
 template <bool ANY>
 __device__ __forceinline__ bool traverse_exact(const SceneView& s, V3 o, V3 dir, double ray_max, Hit& hit) {
@@ -211,25 +215,38 @@ __device__ __forceinline__ void warp_begin_ray(WarpShared& ws, unsigned lane, V3
     ws.pend[lane] = 0u;
 }
 
-// One interior node for one ray: pops the nearest pending child of the node group `ng`, tests its 8 quantised child boxes,
-// leaves the interior children hit in `ng` (octant ordered) and queues the primitives whose box was hit.
-template <class WS>
-__device__ __forceinline__ uint32_t node_step(const SceneView& s, WS& ws, unsigned lane, const WideRay& r, uint2& ng, uint2* stack, int& sp) {
-    const uint32_t bit = 31u - __clz(ng.y);
-    ng.y &= ~(1u << bit);
-    const uint32_t slot = (bit - 24u) ^ r.octinv;
-    const uint32_t child = ng.x + __popc(ng.y & 0xFFu & ((1u << slot) - 1u));
-    if ((ng.y & 0xFF000000u) && sp < kWideStack) stack[sp++] = ng;
-
-    const int4* raw = reinterpret_cast<const int4*>(s.wide_nodes + child);
-    const int4 n0 = __ldg(raw), n1 = __ldg(raw + 1), n2 = __ldg(raw + 2), n3 = __ldg(raw + 3), n4 = __ldg(raw + 4);
+// ---- node phase ------------------------------------------------------------------------------------------------------------
+//
+// A node group (uint2) = { index of the first interior child of some node, hit interior children << 24 | imask }: the children of
+// one node the ray still has to visit, nearest first (bit 31 = nearest in octant order).
+struct NodeData {
+    int4 n0, n1, n2, n3, n4;
     // n0 = px, py, pz, {ex,ey,ez,imask};  n1 = child_base, prim_base, {leafmask, pad}, pad
     // n2 = qlo_x[0..7], qlo_y[0..7];  n3 = qlo_z[0..7], qhi_x[0..7];  n4 = qhi_y[0..7], qhi_z[0..7]
+};
+
+// Removes the nearest pending child from the group and returns its node index.
+__device__ __forceinline__ uint32_t pop_child(uint2& g, uint32_t octinv) {
+    const uint32_t bit = 31u - __clz(g.y);
+    g.y &= ~(1u << bit);
+    const uint32_t slot = (bit - 24u) ^ octinv;
+    return g.x + __popc(g.y & 0xFFu & ((1u << slot) - 1u));
+}
+
+__device__ __forceinline__ NodeData load_node(const SceneView& s, uint32_t index) {
+    const int4* raw = reinterpret_cast<const int4*>(s.wide_nodes + index);
+    NodeData n;
+    n.n0 = __ldg(raw); n.n1 = __ldg(raw + 1); n.n2 = __ldg(raw + 2); n.n3 = __ldg(raw + 3); n.n4 = __ldg(raw + 4);
+    return n;
+}
+
+// The conservative slab test of the ray against the 8 quantised child boxes of one node: bit s of the result = slot s is hit.
+__device__ __forceinline__ uint32_t test_node(const NodeData& n, const WideRay& r) {
+    const int4 n0 = n.n0, n2 = n.n2, n3 = n.n3, n4 = n.n4;
     const uint32_t e_imask = (uint32_t)n0.w;
     const AxisPlanes X = axis_planes(__int_as_float(n0.x), r.ox, r.idx, r.eox, e_imask & 0xFFu);
     const AxisPlanes Y = axis_planes(__int_as_float(n0.y), r.oy, r.idy, r.eoy, (e_imask >> 8) & 0xFFu);
     const AxisPlanes Z = axis_planes(__int_as_float(n0.z), r.oz, r.idz, r.eoz, (e_imask >> 16) & 0xFFu);
-    const uint32_t imask = e_imask >> 24, leafmask = (uint32_t)n1.z & 0xFFu;
     // entry planes: lower bounds for positive directions, upper bounds for negative ones
     const bool negx = !(r.octinv & 4u), negy = !(r.octinv & 2u), negz = !(r.octinv & 1u);
     const uint32_t nx0 = negx ? (uint32_t)n3.z : (uint32_t)n2.x, nx1 = negx ? (uint32_t)n3.w : (uint32_t)n2.y;
@@ -275,24 +292,105 @@ __device__ __forceinline__ uint32_t node_step(const SceneView& s, WS& ws, unsign
         hits |= (tn <= tf ? 1u : 0u) << sl;
     }
 #endif
-    // interior children: bit of slot sl moves to position sl ^ octinv (nearest child in the highest bit)
+    return hits;
+}
+
+// The interior children hit, as a node group: the bit of slot sl moves to position sl ^ octinv (nearest child in the highest bit).
+__device__ __forceinline__ uint2 hit_group(const NodeData& n, uint32_t hits, uint32_t octinv) {
+    const uint32_t imask = (uint32_t)n.n0.w >> 24;
     uint32_t ih = hits & imask;
-    if (r.octinv & 1u) ih = ((ih & 0x55u) << 1) | ((ih & 0xAAu) >> 1);
-    if (r.octinv & 2u) ih = ((ih & 0x33u) << 2) | ((ih & 0xCCu) >> 2);
-    if (r.octinv & 4u) ih = ((ih & 0x0Fu) << 4) | ((ih & 0xF0u) >> 4);
-    ng = make_uint2((uint32_t)n1.x, (ih << 24) | imask);
-    // primitives: one per leaf slot, contiguous from prim_base in ascending slot order
-    uint32_t lh = hits & leafmask;
-    const uint32_t outcome = ih | (lh << 8);   // (work counters of the stats build)
+    if (octinv & 1u) ih = ((ih & 0x55u) << 1) | ((ih & 0xAAu) >> 1);
+    if (octinv & 2u) ih = ((ih & 0x33u) << 2) | ((ih & 0xCCu) >> 2);
+    if (octinv & 4u) ih = ((ih & 0x0Fu) << 4) | ((ih & 0xF0u) >> 4);
+    return make_uint2((uint32_t)n.n1.x, (ih << 24) | imask);
+}
+
+// Queues the primitives of the leaf slots in `lh` (one per slot, contiguous from prim_base in ascending slot order).
+template <class WS>
+__device__ __forceinline__ void push_prims(WS& ws, unsigned lane, uint32_t lh, uint32_t leafmask, uint32_t prim_base) {
     if (lh) {
         const uint32_t n = __popc(lh);
         uint32_t pos = atomicAdd(&ws.tail, n);
         ws.pend[lane] += n;
-        const uint32_t tag = lane << kSlotBits, prim_base = (uint32_t)n1.y;
+        const uint32_t tag = lane << kSlotBits;
         do {
             const uint32_t k = __ffs(lh) - 1u;
             lh &= lh - 1u;
             const uint32_t leaf_slot = prim_base + __popc(leafmask & ((1u << k) - 1u));
+            ws.queue[pos & (kQueue - 1u)] = tag | leaf_slot;
+            pos += 1u;
+        } while (lh);
+    }
+}
+
+// One interior node for one ray: pops the nearest pending child of the node group `ng`, tests its 8 quantised child boxes,
+// leaves the interior children hit in `ng` (octant ordered) and queues the primitives whose box was hit.
+template <class WS>
+__device__ __forceinline__ uint32_t node_step(const SceneView& s, WS& ws, unsigned lane, const WideRay& r, uint2& ng, uint2* stack, int& sp) {
+    const uint32_t child = pop_child(ng, r.octinv);
+    if ((ng.y & 0xFF000000u) && sp < kWideStack) stack[sp++] = ng;
+    const NodeData n = load_node(s, child);
+    const uint32_t hits = test_node(n, r);
+    ng = hit_group(n, hits, r.octinv);
+    const uint32_t leafmask = (uint32_t)n.n1.z & 0xFFu, lh = hits & leafmask;
+    push_prims(ws, lane, lh, leafmask, (uint32_t)n.n1.y);
+    return (ng.y >> 24) | (lh << 8);   // (work counters of the stats build)
+}
+
+// Two nodes for one ray in one step (CRAY_NODE_PAIR): the nearest pending child A and the next one in visit order, B -- the
+// second child of the same group or, if A was its last, the nearest child of the group on top of the stack.  Both records are
+// requested before either is used, so a lane has two dependent-fetch latencies in flight instead of one.  Visit order stays
+// depth-first, nearest first: A's children are visited before B's, B's before the rest of B's group.  B is visited a step early
+// (before A's primitives could have shortened the ray) -- the box test it gets is the one it would have got in the same
+// iteration anyway, since primitive rounds run after the node phase.
+// Lanes without a second pending child run the B half on A's record with its result masked off (no divergence).
+constexpr int kPairStackLimit = kWideStackLimit;   // a pair is only taken while sp + 2 <= this: the unpaired descent below needs
+                                                   // at most one more entry per level, kWideStack = this + kWideStackLimit holds both
+template <class WS>
+__device__ __forceinline__ uint32_t node_step_pair(const SceneView& s, WS& ws, unsigned lane, const WideRay& r, uint2& ng, uint2* stack, int& sp) {
+    const uint32_t a = pop_child(ng, r.octinv);
+    uint32_t b = a;
+    bool have_b = false;
+    if (sp + 2 <= kPairStackLimit) {
+        if (ng.y & 0xFF000000u) {
+            b = pop_child(ng, r.octinv);
+            have_b = true;
+        } else if (sp > 0) {
+            uint2 g = stack[sp - 1];
+            b = pop_child(g, r.octinv);
+            have_b = true;
+            if (g.y & 0xFF000000u) stack[sp - 1] = g;
+            else --sp;
+        }
+    }
+    if ((ng.y & 0xFF000000u) && sp < kWideStack) stack[sp++] = ng;
+    const NodeData na = load_node(s, a), nb = load_node(s, b);
+    const uint32_t hits_a = test_node(na, r);
+    uint32_t hits_b = have_b ? test_node(nb, r) : 0u;
+    // primitives of both nodes in one pass: slots 0..7 = A's, 8..15 = B's
+    const uint32_t lm_a = (uint32_t)na.n1.z & 0xFFu, lm_b = (uint32_t)nb.n1.z & 0xFFu;
+    uint32_t lh = (hits_a & lm_a) | ((hits_b & lm_b) << 8);
+    uint2 gb = hit_group(nb, hits_b, r.octinv);
+    if (__popc(lh) > 15) {
+        // the test queue holds 31 left-over entries + 15 per lane: a lane whose two nodes hit all 16 of their primitives puts B
+        // back as a group of its own (visited again later)
+        lh &= 0xFFu;
+        hits_b = 0u;
+        gb = make_uint2(b, 0x80000000u);
+    }
+    if ((gb.y & 0xFF000000u) && sp < kWideStack) stack[sp++] = gb;
+    ng = hit_group(na, hits_a, r.octinv);
+    const uint32_t outcome = (ng.y >> 24) | ((lh & 0xFFu) << 8) | (have_b ? 0x10000u | ((gb.y >> 24) << 24) | ((lh >> 8) ? 0x20000u : 0u) : 0u);
+    if (lh) {
+        const uint32_t n = __popc(lh);
+        uint32_t pos = atomicAdd(&ws.tail, n);
+        ws.pend[lane] += n;
+        const uint32_t tag = lane << kSlotBits;
+        do {
+            const uint32_t k = __ffs(lh) - 1u;
+            lh &= lh - 1u;
+            const bool second = k >= 8u;
+            const uint32_t leaf_slot = (second ? (uint32_t)nb.n1.y : (uint32_t)na.n1.y) + __popc((second ? lm_b : lm_a) & ((1u << (k & 7u)) - 1u));
             ws.queue[pos & (kQueue - 1u)] = tag | leaf_slot;
             pos += 1u;
         } while (lh);
@@ -317,7 +415,7 @@ __device__ __forceinline__ void prim_round_closest(const SceneView& s, WarpShare
         const V3 dir = mk(ws.dx[owner], ws.dy[owner], ws.dz[owner]);
         const double rmax = ws.tmax[owner];
         double cand = rmax, u, v;
-        verdict = leaf_prim_candidate(s, lp, o, dir, cand, ws.best[owner] != CRAY_NO_HIT, u, v);
+        verdict = leaf_prim_candidate(s, lp, o, dir, cand, ws.best[owner] != CRAY_NO_HIT, u, v, s.wide_prims + slot);
         t = verdict == 1 ? cand : rmax;
     }
     // accepted distances are positive f64: they order like their bit patterns, so one shared-memory atomicMin per
@@ -365,7 +463,12 @@ __device__ __forceinline__ void prim_round_any(const SceneView& s, WarpShared& w
         const LeafPrim lp = load_leaf_prim(s.wide_prims + slot);
         const V3 o = mk(ws.ox[owner], ws.oy[owner], ws.oz[owner]);
         const V3 dir = mk(ws.dx[owner], ws.dy[owner], ws.dz[owner]);
+#if CRAY_PRIM_NOCOPY
+        const bool occ = (lp.kind & 0xFFu) == PRIM_TRIANGLE ? leaf_prim_any(s, lp, o, dir, ws.tmax[owner]) : analytic_any_at(s, s.wide_prims + slot, o, dir, ws.tmax[owner]);
+        if (occ) ws.best[owner] = 1u;
+#else
         if (leaf_prim_any(s, lp, o, dir, ws.tmax[owner])) ws.best[owner] = 1u;
+#endif
     }
     const unsigned grp = __match_any_sync(FULL, act ? owner : 32u + lane);
     if (act && lane == (unsigned)(__ffs(grp) - 1)) ws.pend[owner] -= __popc(grp);

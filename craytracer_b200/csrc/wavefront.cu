@@ -205,6 +205,10 @@ constexpr int kWideMinBlocksAny = CRAY_WIDE_MIN_BLOCKS_ANY;   // the any-hit ins
 constexpr int kWideMinBlocksF32 = CRAY_WIDE_MIN_BLOCKS_F32;   // F32 mode: no f64 triangle test to hold registers for
 
 enum : int { LANE_IDLE = 0, LANE_LIVE = 1, LANE_DRAIN = 2 };
+#ifndef CRAY_NODE_REPS
+#define CRAY_NODE_REPS 6
+#endif
+constexpr int kNodeReps = CRAY_NODE_REPS;   // node phases per iteration of the persistent loop
 
 // Tuning build (make VARIANT=stats EXTRA=-DCRAY_WIDE_STATS=1): work counters of the traversal kernels, read with
 // cray_debug_wide_stats.  [0] rays  [1] warp iterations  [2] node steps (lanes)  [3] node phases (warps)
@@ -222,7 +226,7 @@ __device__ unsigned long long g_wide_stats[2][12];
 #endif
 
 template <bool ANY, class Source, bool F32 = false>
-__global__ void __launch_bounds__(128, F32 ? kWideMinBlocksF32 : (ANY ? kWideMinBlocksAny : kWideMinBlocks)) k_wide_persistent(SceneView s, Source src, const unsigned long long* __restrict__ n_ptr, unsigned long long* cursor, WideTuning tune) {
+__global__ void __launch_bounds__(128, F32 ? kWideMinBlocksF32 : (ANY ? kWideMinBlocksAny : kWideMinBlocks)) k_wide_persistent(const __grid_constant__ SceneView s, const __grid_constant__ Source src, const unsigned long long* __restrict__ n_ptr, unsigned long long* cursor, WideTuning tune) {
     using WS = std::conditional_t<F32, WarpShared32, WarpShared>;
     __shared__ WS shared[4];
     WS& ws = shared[threadIdx.x >> 5];
@@ -274,22 +278,33 @@ __global__ void __launch_bounds__(128, F32 ? kWideMinBlocksF32 : (ANY ? kWideMin
             if (exhausted) break;
             continue;
         }
-        // node phase
+        // node phase(s)
+#pragma unroll 1
+        for (int rep = 0;;) {
         bool stepping = false;
         if (state == LANE_LIVE) {
             if (!(ng.y & 0xFF000000u) && sp > 0) ng = stack[--sp];
             stepping = (ng.y & 0xFF000000u) != 0u;
             uint32_t outcome = 0xFFFFFFFFu;
+#if CRAY_NODE_PAIR
+            if (stepping) outcome = node_step_pair(s, ws, lane, r, ng, stack, sp);
+#else
             if (stepping) outcome = node_step(s, ws, lane, r, ng, stack, sp);
+#endif
 #if CRAY_WIDE_STATS
             {
+                // outcome: interior hits | leaf hits << 8 of node A; paired steps add bit 16 = a node B was visited, bit 17 = B queued
+                // primitives, bits 24.. = B's interior hits
                 const unsigned m = __activemask();
-                WIDE_STAT(8, __popc(__ballot_sync(m, outcome == 0u)));
-                WIDE_STAT(10, __popc(__ballot_sync(m, stepping && (outcome >> 8) == 0u)));
-                WIDE_STAT(11, __popc(__ballot_sync(m, stepping && ws.best[lane] != (ANY ? 0u : CRAY_NO_HIT))));
-                unsigned ihs = stepping ? __popc(outcome & 0xFFu) : 0u;
+                const bool second = CRAY_NODE_PAIR && stepping && (outcome & 0x10000u);
+                const bool a_empty = stepping && (outcome & 0xFFFFu) == 0u, b_empty = second && (outcome >> 24) == 0u && !(outcome & 0x20000u);
+                WIDE_STAT(8, __popc(__ballot_sync(m, a_empty)) + __popc(__ballot_sync(m, b_empty)));
+                WIDE_STAT(10, __popc(__ballot_sync(m, stepping && ((outcome >> 8) & 0xFFu) == 0u)) + __popc(__ballot_sync(m, second && !(outcome & 0x20000u))));
+                WIDE_STAT(11, __popc(__ballot_sync(m, stepping && ws.best[lane] != (ANY ? 0u : CRAY_NO_HIT))) * (1 + 0) + __popc(__ballot_sync(m, second && ws.best[lane] != (ANY ? 0u : CRAY_NO_HIT))));
+                unsigned ihs = stepping ? __popc(outcome & 0xFFu) + (second ? __popc(outcome >> 24) : 0u) : 0u;
                 for (int o = 16; o; o >>= 1) ihs += __shfl_xor_sync(m, ihs, o);
                 WIDE_STAT(9, ihs);
+                WIDE_STAT(2, __popc(__ballot_sync(m, second)));   // (the first node of each step is counted below)
             }
 #else
             (void)outcome;
@@ -306,6 +321,13 @@ __global__ void __launch_bounds__(128, F32 ? kWideMinBlocksF32 : (ANY ? kWideMin
         }
 #endif
         __syncwarp();
+        // CRAY_NODE_REPS > 1: further node phases before the warp-wide bookkeeping below (its ballots, the finish test, the refill
+        // test cost about a third of a node step), as long as no full round of tests is queued -- which also keeps the queue within
+        // its 31 + 32 x 8 entries -- and some lane still has a node to visit
+        if (++rep >= kNodeReps) break;
+        if (*(volatile uint32_t*)&ws.tail - head >= 32u) break;
+        if (!__any_sync(FULL, state == LANE_LIVE && ((ng.y & 0xFF000000u) || sp > 0))) break;
+        }
         // primitive rounds
         uint32_t count = *(volatile uint32_t*)&ws.tail - head;
         if (count) {

@@ -9,11 +9,13 @@ class the launch with the longest duration is taken (the capture window sits whe
 import csv
 import io
 import json
+import re
 import subprocess
 import sys
 
-CLASSES = [("extend", "k_wide_persistent<(bool)0, cray::ExtendSource, (bool)0>"), ("shadow", "k_wide_persistent<(bool)1, cray::ShadowSource, (bool)0>"),
-           ("shade", "k_shade"), ("generate", "k_generate"), ("extend_f32", "k_wide_persistent<(bool)0, cray::ExtendSource, (bool)1>")]
+# (ncu prints template arguments as `(bool)0, cray::ExtendSource` on the source page and as `0, ExtendSource` on the raw page)
+CLASSES = [("extend", r"k_wide_persistent<(\(bool\))?0, (cray::)?ExtendSource, (\(bool\))?0>"), ("shadow", r"k_wide_persistent<(\(bool\))?1, (cray::)?ShadowSource, (\(bool\))?0>"),
+           ("shade", r"k_shade"), ("generate", r"k_generate"), ("extend_f32", r"k_wide_persistent<(\(bool\))?0, (cray::)?ExtendSource, (\(bool\))?1>")]
 
 
 def main():
@@ -36,7 +38,7 @@ def main():
     for key, needle in CLASSES:
         best = None
         for r in rows[2:]:
-            if needle not in r[col["Kernel Name"]]:
+            if not re.search(needle, r[col["Kernel Name"]]):
                 continue
             ms = to_ms(r[col["gpu__time_duration.sum"]], units[col["gpu__time_duration.sum"]])
             if best is None or ms > best[0]:
