@@ -423,6 +423,56 @@ def run_ours(args):
     return 0
 
 
+def run_single_process(args):
+    """All N GPUs from ONE process through the C ABI a Rust host would call: cray_scene_create_multi (one host-side BVH build,
+    uploaded to every device) + cray_render_multi (a thread per device, sample ranges sharded, one ncclReduce of the films).
+    `value` divides by the slowest GPU's CUDA-event time of each frame (the reduce excluded), `e2e` by the host's wall clock
+    around the synchronous call (reduce and the copy of the film to host memory included)."""
+    import torch
+
+    import craytracer_b200 as c
+    if not torch.cuda.is_available() or torch.cuda.device_count() < args.gpus:
+        raise SystemExit(f"bench.py --single-process: {args.gpus} CUDA devices needed")
+    hs, parse_s = build_host_scene(args)
+    t0 = time.time()
+    replicas = c.Scene.create_multi(hs, list(range(args.gpus)), build=c.BUILD_EXACT | c.BUILD_FAST | (c.BUILD_F32 if args.mode == "f32" else 0))
+    create_s = time.time() - t0
+    mode = {"exact": c.TRAVERSE_EXACT, "fast": c.TRAVERSE_FAST, "f32": c.TRAVERSE_F32}[args.mode]
+    for k in range(args.warmup):
+        c.render_multi(replicas, seed=1000 + k, sample_begin=0, sample_end=args.spp, mode=mode)
+    sampler = ClockSampler(0)
+    sampler.start()
+    rays = traced = launches = 0
+    device_ms = wall_ms = 0.0
+    for k in range(args.steps):
+        t_host = time.perf_counter()
+        _, st = c.render_multi(replicas, seed=k, sample_begin=0, sample_end=args.spp, mode=mode)
+        wall_ms += (time.perf_counter() - t_host) * 1e3
+        device_ms += st.render_ms
+        rays += st.closest_rays + st.shadow_rays
+        traced += st.closest_rays + st.shadow_rays_traced
+        launches += st.kernel_launches
+    clocks = sampler.stop()
+    samples = args.width * args.height * args.spp * args.steps
+    n_film = args.width * args.height * 3
+    info = replicas[0].info
+    emit({"metric": "Mrays/s on dragon.cry", "value": rays / device_ms / 1e3, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+          "ms_per_step": device_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+          "launch": "single process: cray_scene_create_multi + cray_render_multi (include/cray_b200.h)",
+          "config": {"workload": WORKLOAD, "spp": args.spp, "max_depth": 8, "sampler": "sobol", "traversal": args.mode, "parallelism": f"samples/{args.gpus}"},
+          "value_counts": "reference rays = Scene::intersect + Scene::intersects calls of the reference for the same samples",
+          "rays": {"reference_mrays_per_s": rays / device_ms / 1e3, "traced_mrays_per_s": traced / device_ms / 1e3},
+          "samples_per_s": samples / (device_ms * 1e-3),
+          "e2e": {"value": rays / wall_ms / 1e3, "unit": "Mrays/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": n_film * 4, "samples_per_s": samples / (wall_ms * 1e-3),
+                  "ms_per_step": wall_ms / args.steps, "note": "host wall clock around cray_render_multi: render on every GPU, ncclReduce, film to host memory"},
+          "gpu_launches": int(launches), "clocks": clocks,
+          "setup": {"parse_and_standin_s": parse_s, "bvh_build_ms": info.bvh_build_ms, "upload_ms": info.upload_ms, "scene_create_s": create_s,
+                    "note": "ONE host-side BVH build for all devices (under torchrun every rank builds its own)"}})
+    for r in replicas:
+        r.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -438,10 +488,14 @@ def main():
                     help="fast (default) and exact return the reference's hits bit for bit; f32 is the opt-in fast mode of SURVEY 8f n4")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of host work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--single-process", action="store_true",
+                    help="drive all --gpus devices from this one process through cray_scene_create_multi / cray_render_multi instead of one rank per GPU")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
+    if args.single_process:
+        return run_single_process(args)
     return run_ours(args)
 
 
