@@ -100,9 +100,24 @@ struct SurfaceSample {  // bxdf.rs:12-19
 __device__ __forceinline__ bool lobe_has_reflection(const DevLobe& l) { return l.kind != LOBE_SPECULAR_BTDF; }
 __device__ __forceinline__ bool lobe_has_transmission(const DevLobe& l) { return l.kind == LOBE_SPECULAR_BTDF || l.kind == LOBE_FRESNEL_SPECULAR; }
 
+// The shading kernels are instantiated per shade class (k_shade_class, wavefront.cu): LOBES is the set of lobe kinds a material of
+// that class can hold (bit k = lobe kind k), so each kernel carries only its own family's code and registers.
+__host__ __device__ constexpr uint32_t lobe_bit(uint32_t kind) { return 1u << kind; }
+constexpr uint32_t kLobesAll = 0x3Fu;
+constexpr uint32_t kLobesDiffuse = lobe_bit(LOBE_LAMBERTIAN) | lobe_bit(LOBE_OREN_NAYAR);
+// Material::new_* material.rs:20-70 (make_material, scene_device.cu): matte, glass, plastic, metal
+__host__ __device__ constexpr uint32_t lobes_of_class(uint32_t cls) {
+    return cls == CRAY_MAT_MATTE ? kLobesDiffuse
+         : cls == CRAY_MAT_GLASS ? lobe_bit(LOBE_FRESNEL_SPECULAR)
+         : cls == CRAY_MAT_PLASTIC ? (kLobesDiffuse | lobe_bit(LOBE_SPECULAR_BRDF))
+         : cls == CRAY_MAT_METAL ? lobe_bit(LOBE_CONDUCTOR) : kLobesAll;
+}
+
 // BxDF::f bxdf.rs:214-265
-__device__ __noinline__ Color3 lobe_f(const SceneView& s, const DevLobe& l, V3 w_o, V3 w_i, V3 normal, double tu, double tv) {
+template <uint32_t LOBES = kLobesAll>
+__device__ __forceinline__ Color3 lobe_f_inline(const SceneView& s, const DevLobe& l, V3 w_o, V3 w_i, V3 normal, double tu, double tv) {
     const Color3 black = mkc(0.0, 0.0, 0.0);
+    if constexpr (!(LOBES & kLobesDiffuse)) return black;
     if (l.kind == LOBE_LAMBERTIAN) {
         if (same_hemisphere(normal, w_o, w_i)) return eval_color(s, l.t0, tu, tv) * kFrac1Pi;
         return black;
@@ -134,78 +149,101 @@ __device__ __noinline__ Color3 lobe_f(const SceneView& s, const DevLobe& l, V3 w
     }
     return black;
 }
+// Out of line where a class calls it from several places (plastic: two lobes; the generic instantiation), inline where the class has
+// one lobe and one call site.
+template <uint32_t LOBES>
+__device__ __noinline__ Color3 lobe_f_outline(const SceneView& s, const DevLobe& l, V3 w_o, V3 w_i, V3 normal, double tu, double tv) {
+    return lobe_f_inline<LOBES>(s, l, w_o, w_i, normal, tu, tv);
+}
+__host__ __device__ constexpr bool lobes_single_family(uint32_t lobes) { return lobes == kLobesDiffuse || (lobes & (lobes - 1u)) == 0u; }
+template <uint32_t LOBES = kLobesAll>
+__device__ __forceinline__ Color3 lobe_f(const SceneView& s, const DevLobe& l, V3 w_o, V3 w_i, V3 normal, double tu, double tv) {
+    if constexpr (lobes_single_family(LOBES)) return lobe_f_inline<LOBES>(s, l, w_o, w_i, normal, tu, tv);
+    else return lobe_f_outline<LOBES>(s, l, w_o, w_i, normal, tu, tv);
+}
 // BxDF::pdf bxdf.rs:269-284
 __device__ __forceinline__ PdfValue lobe_pdf(const DevLobe& l, V3 w_i, V3 normal) {
     if (l.kind == LOBE_LAMBERTIAN || l.kind == LOBE_OREN_NAYAR) return non_delta(kFrac1Pi * fabs(dot(w_i, normal)));
     return delta_pdf();
 }
 // BxDF::sample bxdf.rs:83-209
-__device__ __noinline__ bool lobe_sample(const SceneView& s, const DevLobe& l, const VertexSamples& vs, V3 w_o, V3 normal, double tu, double tv,
-                                         SurfaceSample& out, bool& assert_failed) {
-    switch (l.kind) {
-        case LOBE_LAMBERTIAN:
-        case LOBE_OREN_NAYAR: {
-            V3 w_i = cosine_sample_hemisphere(vs.get(VertexSamples::MATERIAL_U), vs.get(VertexSamples::MATERIAL_V), normal, assert_failed);
-            if (dot(normal, w_o) < 0.0) w_i = neg(w_i);
-            out.w_i = w_i;
-            out.f = lobe_f(s, l, w_o, w_i, normal, tu, tv);
-            out.pdf = lobe_pdf(l, w_i, normal);
-            out.is_specular = false;
-            return true;
-        }
-        case LOBE_CONDUCTOR: {
-            const V3 w_i = reflect(w_o, normal);
-            if (!(fabs(magnitude(w_i) - 1.0) <= kEpsilon)) assert_failed = true;  // assert_abs_diff_eq! bxdf.rs:119
-            const double cos_theta_i = fabs(dot(w_o, normal));
-            const Color3 fr = fresnel_conductor(mkc(1.0, 1.0, 1.0), eval_color(s, l.t0, tu, tv), eval_color(s, l.t1, tu, tv), cos_theta_i);
-            out.w_i = w_i;
-            out.f = fr / cos_theta_i;
-            out.pdf = delta_pdf();
-            out.is_specular = true;
-            return true;
-        }
-        case LOBE_SPECULAR_BRDF: {
-            const V3 w_i = reflect(w_o, normal);
-            if (!(fabs(magnitude(w_i) - 1.0) <= kEpsilon)) assert_failed = true;
-            const double cos_theta_i = fabs(dot(w_o, normal));
-            const Color3 fr = mkc(1.0, 1.0, 1.0) * fresnel_dielectric(l.eta_i, l.eta_t, cos_theta_i);
-            out.w_i = w_i;
-            out.f = eval_color(s, l.t0, tu, tv) * fr / fabs(cos_theta_i);
-            out.pdf = delta_pdf();
-            out.is_specular = true;
-            return true;
-        }
-        case LOBE_SPECULAR_BTDF: {
-            const double cos_theta_i = fabs(dot(w_o, normal));
-            V3 w_i;
-            if (!refract(w_o, normal, cos_theta_i, l.eta_i, l.eta_t, w_i)) return false;
-            if (!(fabs(magnitude(w_i) - 1.0) <= kEpsilon)) assert_failed = true;
-            const double fr = fresnel_dielectric(l.eta_i, l.eta_t, cos_theta_i);
-            out.w_i = w_i;
-            out.f = eval_color(s, l.t1, tu, tv) * (1.0 - fr) / cos_theta_i;
-            out.pdf = delta_pdf();
-            out.is_specular = true;
-            return true;
-        }
-        default: {  // LOBE_FRESNEL_SPECULAR bxdf.rs:176-207
-            const double cos_theta_i = dot(w_o, normal);
-            const double fresnel_reflectance = fresnel_dielectric(l.eta_i, l.eta_t, cos_theta_i);
-            if (vs.get(VertexSamples::MATERIAL_U) < fresnel_reflectance) {
-                out.w_i = reflect(w_o, normal);
-                out.f = eval_color(s, l.t0, tu, tv) * fresnel_reflectance / fabs(cos_theta_i);
-                out.pdf = non_delta(fresnel_reflectance);
-                out.is_specular = true;
-                return true;
-            }
-            V3 w_i;
-            if (!refract(w_o, normal, cos_theta_i, l.eta_i, l.eta_t, w_i)) return false;
-            out.w_i = w_i;
-            out.f = eval_color(s, l.t1, tu, tv) * (1.0 - fresnel_reflectance) / fabs(cos_theta_i);
-            out.pdf = non_delta(1.0 - fresnel_reflectance);
-            out.is_specular = true;
-            return true;
-        }
+template <uint32_t LOBES = kLobesAll>
+__device__ __forceinline__ bool lobe_sample_inline(const SceneView& s, const DevLobe& l, const VertexSamples& vs, V3 w_o, V3 normal, double tu, double tv,
+                                                   SurfaceSample& out, bool& assert_failed) {
+    if ((LOBES & kLobesDiffuse) && (l.kind == LOBE_LAMBERTIAN || l.kind == LOBE_OREN_NAYAR)) {
+        V3 w_i = cosine_sample_hemisphere(vs.get(VertexSamples::MATERIAL_U), vs.get(VertexSamples::MATERIAL_V), normal, assert_failed);
+        if (dot(normal, w_o) < 0.0) w_i = neg(w_i);
+        out.w_i = w_i;
+        out.f = lobe_f<LOBES>(s, l, w_o, w_i, normal, tu, tv);
+        out.pdf = lobe_pdf(l, w_i, normal);
+        out.is_specular = false;
+        return true;
     }
+    if ((LOBES & lobe_bit(LOBE_CONDUCTOR)) && l.kind == LOBE_CONDUCTOR) {
+        const V3 w_i = reflect(w_o, normal);
+        if (!(fabs(magnitude(w_i) - 1.0) <= kEpsilon)) assert_failed = true;  // assert_abs_diff_eq! bxdf.rs:119
+        const double cos_theta_i = fabs(dot(w_o, normal));
+        const Color3 fr = fresnel_conductor(mkc(1.0, 1.0, 1.0), eval_color(s, l.t0, tu, tv), eval_color(s, l.t1, tu, tv), cos_theta_i);
+        out.w_i = w_i;
+        out.f = fr / cos_theta_i;
+        out.pdf = delta_pdf();
+        out.is_specular = true;
+        return true;
+    }
+    if ((LOBES & lobe_bit(LOBE_SPECULAR_BRDF)) && l.kind == LOBE_SPECULAR_BRDF) {
+        const V3 w_i = reflect(w_o, normal);
+        if (!(fabs(magnitude(w_i) - 1.0) <= kEpsilon)) assert_failed = true;
+        const double cos_theta_i = fabs(dot(w_o, normal));
+        const Color3 fr = mkc(1.0, 1.0, 1.0) * fresnel_dielectric(l.eta_i, l.eta_t, cos_theta_i);
+        out.w_i = w_i;
+        out.f = eval_color(s, l.t0, tu, tv) * fr / fabs(cos_theta_i);
+        out.pdf = delta_pdf();
+        out.is_specular = true;
+        return true;
+    }
+    if ((LOBES & lobe_bit(LOBE_SPECULAR_BTDF)) && l.kind == LOBE_SPECULAR_BTDF) {
+        const double cos_theta_i = fabs(dot(w_o, normal));
+        V3 w_i;
+        if (!refract(w_o, normal, cos_theta_i, l.eta_i, l.eta_t, w_i)) return false;
+        if (!(fabs(magnitude(w_i) - 1.0) <= kEpsilon)) assert_failed = true;
+        const double fr = fresnel_dielectric(l.eta_i, l.eta_t, cos_theta_i);
+        out.w_i = w_i;
+        out.f = eval_color(s, l.t1, tu, tv) * (1.0 - fr) / cos_theta_i;
+        out.pdf = delta_pdf();
+        out.is_specular = true;
+        return true;
+    }
+    if constexpr ((LOBES & lobe_bit(LOBE_FRESNEL_SPECULAR)) != 0u) {  // LOBE_FRESNEL_SPECULAR bxdf.rs:176-207 (the last kind)
+        const double cos_theta_i = dot(w_o, normal);
+        const double fresnel_reflectance = fresnel_dielectric(l.eta_i, l.eta_t, cos_theta_i);
+        if (vs.get(VertexSamples::MATERIAL_U) < fresnel_reflectance) {
+            out.w_i = reflect(w_o, normal);
+            out.f = eval_color(s, l.t0, tu, tv) * fresnel_reflectance / fabs(cos_theta_i);
+            out.pdf = non_delta(fresnel_reflectance);
+            out.is_specular = true;
+            return true;
+        }
+        V3 w_i;
+        if (!refract(w_o, normal, cos_theta_i, l.eta_i, l.eta_t, w_i)) return false;
+        out.w_i = w_i;
+        out.f = eval_color(s, l.t1, tu, tv) * (1.0 - fresnel_reflectance) / fabs(cos_theta_i);
+        out.pdf = non_delta(1.0 - fresnel_reflectance);
+        out.is_specular = true;
+        return true;
+    }
+    return false;  // (a lobe kind outside LOBES: scene_device.cu never builds one for this class)
+}
+
+template <uint32_t LOBES>
+__device__ __noinline__ bool lobe_sample_outline(const SceneView& s, const DevLobe& l, const VertexSamples& vs, V3 w_o, V3 normal, double tu, double tv,
+                                                 SurfaceSample& out, bool& assert_failed) {
+    return lobe_sample_inline<LOBES>(s, l, vs, w_o, normal, tu, tv, out, assert_failed);
+}
+template <uint32_t LOBES = kLobesAll>
+__device__ __forceinline__ bool lobe_sample(const SceneView& s, const DevLobe& l, const VertexSamples& vs, V3 w_o, V3 normal, double tu, double tv,
+                                            SurfaceSample& out, bool& assert_failed) {
+    if constexpr (lobes_single_family(LOBES)) return lobe_sample_inline<LOBES>(s, l, vs, w_o, normal, tu, tv, out, assert_failed);
+    else return lobe_sample_outline<LOBES>(s, l, vs, w_o, normal, tu, tv, out, assert_failed);
 }
 
 __device__ __forceinline__ bool lobe_relevant(const DevLobe& l, bool is_reflecting) {  // bsdf.rs:66-76
@@ -213,12 +251,13 @@ __device__ __forceinline__ bool lobe_relevant(const DevLobe& l, bool is_reflecti
 }
 
 // Material::f material.rs:84-89, BSDF::f bsdf.rs:79-85
+template <uint32_t LOBES = kLobesAll>
 __device__ __forceinline__ Color3 material_f(const SceneView& s, const DevMaterial& m, V3 w_o, V3 w_i, V3 normal, double tu, double tv) {
-    if (!m.is_bsdf) return lobe_f(s, m.lobes[0], w_o, w_i, normal, tu, tv);
+    if (!m.is_bsdf) return lobe_f<LOBES>(s, m.lobes[0], w_o, w_i, normal, tu, tv);
     Color3 acc = mkc(0.0, 0.0, 0.0);
     const bool is_reflecting = dot(w_o, normal) * dot(w_i, normal) > 0.0;
     for (uint32_t i = 0; i < m.n_lobes; ++i)
-        if (lobe_relevant(m.lobes[i], is_reflecting)) acc = acc + lobe_f(s, m.lobes[i], w_o, w_i, normal, tu, tv);
+        if (lobe_relevant(m.lobes[i], is_reflecting)) acc = acc + lobe_f<LOBES>(s, m.lobes[i], w_o, w_i, normal, tu, tv);
     return acc;
 }
 // Material::pdf material.rs:90-95, BSDF::pdf bsdf.rs:87-98
@@ -236,21 +275,22 @@ __device__ __forceinline__ PdfValue material_pdf(const DevMaterial& m, V3 w_o, V
     return delta_pdf();
 }
 // Material::sample material.rs:72-83, BSDF::sample bsdf.rs:15-60
+template <uint32_t LOBES = kLobesAll>
 __device__ __forceinline__ bool material_sample(const SceneView& s, const DevMaterial& m, const VertexSamples& vs, V3 w_o, V3 normal,
                                                 double tu, double tv, SurfaceSample& out, bool& assert_failed) {
-    if (!m.is_bsdf) return lobe_sample(s, m.lobes[0], vs, w_o, normal, tu, tv, out, assert_failed);
+    if (!m.is_bsdf) return lobe_sample<LOBES>(s, m.lobes[0], vs, w_o, normal, tu, tv, out, assert_failed);
     if (m.n_lobes == 0) return false;
     // one lobe: floor(u * 1) is 0 for every u in [0, 1)
     const uint32_t sample_index = m.n_lobes == 1 ? 0u : (uint32_t)as_usize(vs.get(VertexSamples::MATERIAL_1D) * (double)m.n_lobes);
     SurfaceSample smp;
-    if (!lobe_sample(s, m.lobes[sample_index], vs, w_o, normal, tu, tv, smp, assert_failed)) return false;
+    if (!lobe_sample<LOBES>(s, m.lobes[sample_index], vs, w_o, normal, tu, tv, smp, assert_failed)) return false;
     if (!smp.pdf.delta) {
         double pdf = smp.pdf.value;
         Color3 f = smp.f;
         const bool is_reflecting = dot(w_o, normal) * dot(smp.w_i, normal) > 0.0;
         for (uint32_t i = 0; i < m.n_lobes; ++i) {
             if (i == sample_index || !lobe_relevant(m.lobes[i], is_reflecting)) continue;
-            f = f + lobe_f(s, m.lobes[i], w_o, smp.w_i, normal, tu, tv);
+            f = f + lobe_f<LOBES>(s, m.lobes[i], w_o, smp.w_i, normal, tu, tv);
             const PdfValue op = lobe_pdf(m.lobes[i], smp.w_i, normal);
             if (!op.delta) pdf += op.value;
         }

@@ -49,6 +49,8 @@ struct Pool {  // structure-of-arrays over `capacity` path slots
     // front; rays that start in a contact shell (state bit 19, fast and F32 modes) go to the reference-order traversal and fill the
     // same array from the back (entry k at capacity - 1 - k): the two never meet, there is at most one entry per slot.
     uint32_t *extend_queue, *shadow_queue;
+    // the shade stage's queues: kKeyNone arrays of `capacity` entries, one per (shade class, shape kind) key and one for the misses
+    uint32_t* class_queue;
 };
 constexpr uint32_t kStateContact = 1u << 19;
 
@@ -75,6 +77,7 @@ struct Counters {
     unsigned long long n_extend, n_shadow;          // queue lengths (front part)
     unsigned long long extend_cursor, shadow_cursor;  // persistent-kernel fetch positions
     unsigned long long n_extend_contact, n_shadow_contact;  // queue lengths (back part)
+    unsigned long long class_count[16];             // lengths of the shade stage's queues (k_shade_classify)
 };
 
 __device__ __forceinline__ uint32_t st_state(uint32_t s) { return s & 0xFFu; }
@@ -590,6 +593,7 @@ __global__ void k_begin_iteration(Counters* c) {
     c->shadow_traced += c->n_shadow + c->n_shadow_contact;
     c->contact_rays += c->n_extend_contact + c->n_shadow_contact;
     c->n_extend = 0; c->n_shadow = 0; c->extend_cursor = 0; c->shadow_cursor = 0; c->n_extend_contact = 0; c->n_shadow_contact = 0;
+    for (int k = 0; k < 16; ++k) c->class_count[k] = 0;
 }
 
 // BACK: the contact rays of the fast mode (back part of the queue); their hits are reported as wide leaf slots, which is what
@@ -607,98 +611,92 @@ __global__ void __launch_bounds__(128) k_extend_exact(SceneView s, Pool p, const
     }
 }
 
-// One iteration of the `while` loop of estimate_Li (path_integrator.rs:54-212) for one path.
+// The shade stage: one iteration of the `while` loop of estimate_Li (path_integrator.rs:54-212) for every path of the iteration.
 //
-// Paths of one block are first grouped by (shade class, shape kind) of what they hit -- a counting sort of the block's 256
-// queue entries in shared memory -- so that the lanes of a warp run the same material / surface code.
+//   k_shade_classify   every block counting-sorts its 256 consecutive queue entries by (shade class, shape kind) of what they hit
+//                      and appends each group to that key's queue (one atomic per block and key).  Within a key the entries stay in
+//                      runs of ascending slots, so the structure-of-arrays path state is still read and written sector-wise.
+//   k_shade_class<C>   one kernel per shade class (matte, glass, plastic, metal) over its three shape queues: each carries only its
+//                      own material family's code and registers (a conductor vertex runs no light sampling code at all)
+//   k_shade_miss       the paths that left the scene
 #ifndef CRAY_SHADE_THREADS
 #define CRAY_SHADE_THREADS 256
 #endif
-#ifndef CRAY_SHADE_BLOCKS
-#define CRAY_SHADE_BLOCKS 4
-#endif
-#ifndef CRAY_SHADE_PREFETCH
-#define CRAY_SHADE_PREFETCH 1
-#endif
-#ifndef CRAY_SHADE_STATE_PREFETCH
-#define CRAY_SHADE_STATE_PREFETCH 0
-#endif
 constexpr uint32_t kShadeThreads = CRAY_SHADE_THREADS;
 constexpr uint32_t kShadeKeys = 16;   // class (matte, glass, plastic, metal) x shape kind (3); 12 = miss; 13 = no path
+constexpr uint32_t kKeyMiss = 12u, kKeyNone = 13u;
 
-__global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(const __grid_constant__ SceneView s, const __grid_constant__ Pool p, const __grid_constant__ Job job, Counters* counters) {
+__global__ void __launch_bounds__(kShadeThreads) k_shade_classify(const __grid_constant__ SceneView s, const __grid_constant__ Pool p, const __grid_constant__ Job job, Counters* counters) {
     constexpr uint32_t kWarps = kShadeThreads / 32, kCells = kShadeKeys * kWarps;  // 128 (key, warp) cells
     __shared__ uint32_t s_count[kCells];
     __shared__ uint32_t s_warp_total[kCells / 32];
     __shared__ uint32_t s_order[kShadeThreads];
+    __shared__ uint8_t s_key[kShadeThreads];
+    __shared__ uint32_t s_start[kShadeKeys + 1];
+    __shared__ unsigned long long s_base[kShadeKeys];
     // the iteration's rays: the wide traversal's (front of the queue), then the reference-order traversal's (back of it)
     const uint64_t n_front = counters->n_extend;
     const uint64_t n_extend = n_front + counters->n_extend_contact;
     if ((uint64_t)blockIdx.x * kShadeThreads >= n_extend) return;  // whole block idle
-    uint32_t i, slot;
-    {
-        const uint64_t q = (uint64_t)blockIdx.x * kShadeThreads + threadIdx.x;
-        const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-        uint32_t mine = 0xFFFFFFFFu, key = 13u;
-        if (q < n_extend) {
-            mine = p.extend_queue[q < n_front ? (uint32_t)q : p.capacity - 1u - (uint32_t)(q - n_front)];
-#if CRAY_SHADE_STATE_PREFETCH
-            // the path state of this block's 256 slots is read after the sort by whichever thread gets the path: ask for the lines now
-            {
-                const double* const arrays[] = {p.ox, p.oy, p.oz, p.dx, p.dy, p.dz, p.L_r, p.L_g, p.L_b, p.beta_r, p.beta_g, p.beta_b, p.prev_bsdf_pdf, p.hit_t};
-#pragma unroll
-                for (int a = 0; a < 14; ++a) asm volatile("prefetch.global.L1 [%0];" ::"l"(arrays[a] + mine));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.state + mine));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.shuffled_rev + mine));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.hash + mine));
-            }
-#endif
-            const uint32_t my_slot = p.hit_slot[mine];
-            key = 12u;
-            if (my_slot != CRAY_NO_HIT) {
-                const LeafPrim* rec = (job.exact ? s.bin_prims : s.wide_prims) + my_slot;
-                const uint2 prim_kind = __ldg(reinterpret_cast<const uint2*>(&rec->prim));
-                const uint32_t kind = prim_kind.y;
-                key = ((kind >> 8) & 3u) * 3u + (kind & 3u);
-#if CRAY_SHADE_PREFETCH
-                // whichever thread of this block shades the path will read the intersection record and, for a triangle, the first
-                // sector of its shading record: start those loads now, a sort and two barriers ahead of their use
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(rec));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(rec) + 64));
-                if ((kind & 0xFFu) == PRIM_TRIANGLE) asm volatile("prefetch.global.L1 [%0];" ::"l"(s.tri_shade + prim_kind.x));
-#endif
-            }
+    const uint64_t q = (uint64_t)blockIdx.x * kShadeThreads + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t mine = 0xFFFFFFFFu, key = kKeyNone;
+    if (q < n_extend) {
+        mine = p.extend_queue[q < n_front ? (uint32_t)q : p.capacity - 1u - (uint32_t)(q - n_front)];
+        const uint32_t my_slot = p.hit_slot[mine];
+        key = kKeyMiss;
+        if (my_slot != CRAY_NO_HIT) {
+            const LeafPrim* rec = (job.exact ? s.bin_prims : s.wide_prims) + my_slot;
+            const uint32_t kind = __ldg(&rec->kind);
+            key = ((kind >> 8) & 3u) * 3u + (kind & 3u);
         }
-        if (threadIdx.x < kCells) s_count[threadIdx.x] = 0u;
-        __syncthreads();
-        const unsigned grp = __match_any_sync(0xFFFFFFFFu, key);
-        if (lane == (unsigned)(__ffs(grp) - 1)) s_count[key * kWarps + warp] = __popc(grp);
-        __syncthreads();
-        // exclusive scan of the cells in (key, warp) order: the first kCells / 32 warps scan 32 cells each
-        uint32_t cell = 0, incl = 0;
-        if (threadIdx.x < kCells) {
-            cell = s_count[threadIdx.x];
-            incl = cell;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= (unsigned)d) incl += up;
-            }
-            if (lane == 31u) s_warp_total[warp] = incl;
-        }
-        __syncthreads();
-        if (threadIdx.x < kCells) {
-            uint32_t before = 0;
-            for (uint32_t w = 0; w < warp; ++w) before += s_warp_total[w];
-            s_count[threadIdx.x] = before + incl - cell;
-        }
-        __syncthreads();
-        s_order[s_count[key * kWarps + warp] + __popc(grp & ((1u << lane) - 1u))] = mine;
-        __syncthreads();
-        i = s_order[threadIdx.x];
-        if (i == 0xFFFFFFFFu) return;
-        slot = p.hit_slot[i];
     }
+    if (threadIdx.x < kCells) s_count[threadIdx.x] = 0u;
+    __syncthreads();
+    const unsigned grp = __match_any_sync(0xFFFFFFFFu, key);
+    if (lane == (unsigned)(__ffs(grp) - 1)) s_count[key * kWarps + warp] = __popc(grp);
+    __syncthreads();
+    // exclusive scan of the cells in (key, warp) order: the first kCells / 32 warps scan 32 cells each
+    uint32_t cell = 0, incl = 0;
+    if (threadIdx.x < kCells) {
+        cell = s_count[threadIdx.x];
+        incl = cell;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= (unsigned)d) incl += up;
+        }
+        if (lane == 31u) s_warp_total[warp] = incl;
+    }
+    __syncthreads();
+    if (threadIdx.x < kCells) {
+        uint32_t before = 0;
+        for (uint32_t w = 0; w < warp; ++w) before += s_warp_total[w];
+        const uint32_t excl = before + incl - cell;
+        s_count[threadIdx.x] = excl;
+        if (threadIdx.x % kWarps == 0u) s_start[threadIdx.x / kWarps] = excl;   // first entry of each key in the sorted block
+    }
+    if (threadIdx.x == 0) s_start[kShadeKeys] = kShadeThreads;
+    __syncthreads();
+    {
+        const uint32_t pos = s_count[key * kWarps + warp] + __popc(grp & ((1u << lane) - 1u));
+        s_order[pos] = mine;
+        s_key[pos] = (uint8_t)key;
+    }
+    // one atomic per key claims the block's range in that key's queue
+    if (threadIdx.x < kKeyNone) {
+        const uint32_t cnt = s_start[threadIdx.x + 1] - s_start[threadIdx.x];
+        s_base[threadIdx.x] = cnt ? atomicAdd(&counters->class_count[threadIdx.x], (unsigned long long)cnt) : 0ull;
+    }
+    __syncthreads();
+    const uint32_t k = s_key[threadIdx.x];
+    if (k < kKeyNone) p.class_queue[(uint64_t)k * p.capacity + s_base[k] + (threadIdx.x - s_start[k])] = s_order[threadIdx.x];
+}
+
+// One path vertex on a primitive of shade class CLS.
+template <uint32_t CLS>
+__device__ __forceinline__ void shade_vertex(const SceneView& s, const Pool& p, const Job& job, Counters* counters, uint32_t i, uint32_t slot) {
+    constexpr uint32_t LOBES = lobes_of_class(CLS);
     uint32_t st = p.state[i];
     const uint32_t bounces = st_bounces(st);
     const bool is_specular_bounce = (st >> 16) & 1u;
@@ -713,23 +711,6 @@ __global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(cons
         p.L_r[i] = Lf.r; p.L_g[i] = Lf.g; p.L_b[i] = Lf.b;
         p.state[i] = SLOT_DONE | (bounces << 8) | ((shadow_pending ? 1u : 0u) << 17) | ((bad ? 1u : 0u) << 18);
     };
-
-    if (slot == CRAY_NO_HIT) {  // path_integrator.rs:60-90
-        for (uint32_t li = 0; li < s.n_lights; ++li) {
-            const DevLight& light = s.lights[li];
-            if (light.kind != CRAY_LIGHT_INFINITE) continue;  // Light::Le is black for every other kind (light.rs:161-168)
-            const Color3 Le = mkc(light.color[0], light.color[1], light.color[2]);
-            if (is_specular_bounce) {
-                L = L + beta * Le;
-            } else if (!is_black(Le)) {
-                const double light_pdf = (kFrac1Pi / 4.0) * light_pick_pdf(s, li);
-                const double weight = power_heuristic(light_pdf, prev_bsdf_pdf);
-                L = L + beta * Le * weight;
-            }
-        }
-        finish(L, false);
-        return;
-    }
 
     const LeafPrim lp = load_leaf_prim((job.exact ? s.bin_prims : s.wide_prims) + slot);
     V3 location, normal;
@@ -752,13 +733,15 @@ __global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(cons
         material_index = prim.material; area_light = prim.area_light;
     }
     const DevMaterial& material = s.materials[material_index];
+    // every lobe perfectly specular (glass, metal): known at compile time for those classes
+    const bool all_delta = CLS == CRAY_MAT_GLASS || CLS == CRAY_MAT_METAL ? true : (CLS == CRAY_MAT_MATTE ? false : material.all_delta != 0u);
     surface_at(s, lp, ro, rd, hit_t, bu, bv, location, normal, tu, tv, material.needs_uv != 0u);
 
     // PathSegmentSamples::from path_integrator.rs:25-36 -- dimensions 4 + 8 * bounces ... (evaluated where consumed)
     const VertexSamples vs{job.sobol, p.shuffled_rev[i], p.hash[i], 4u + 8u * bounces};
 
-    // emission (:106-126)
-    if (area_light >= 0) {
+    // emission (:106-126); an emitting primitive carries the black matte (primitive.rs:43-46), so it is only ever met by the matte class
+    if (CLS == CRAY_MAT_MATTE && area_light >= 0) {
         const DevLight& light = s.lights[area_light];
         const Color3 Le = mkc(light.color[0], light.color[1], light.color[2]);
         if (!is_black(Le)) {
@@ -780,14 +763,14 @@ __global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(cons
     // Both rays of this vertex start at `location`.  If it lies in the outer shell of a marked node box, only the reference-order
     // traversal reproduces what the reference's box test does to them (bvh_build.hpp "planar contact"); directions are unit vectors.
     const bool contact = !job.exact && (lp.kind & kKindContact) && origin_in_contact_shell(s, location, kContactTol);
-    if (!material.all_delta) {
+    if (!all_delta) {
         double light_sampler_pdf;
         // a single light is picked whatever the sample value is (the search of light.rs:203-211 ends at 0 for every u < 1)
         const uint32_t light_index = light_pick(s, s.n_lights > 1 ? vs.get(VertexSamples::LIGHT_INDEX) : 0.0, light_sampler_pdf);
         const DevLight& light = s.lights[light_index];
         const LightSample ls = light_sample_li(s, light, vs, location, normal, bad);
         Color3 contribution = mkc(0.0, 0.0, 0.0);
-        const Color3 f = material_f(s, material, w_o, ls.w_i, normal, tu, tv);
+        const Color3 f = material_f<LOBES>(s, material, w_o, ls.w_i, normal, tu, tv);
         const double cos_theta = fabs(dot(ls.w_i, normal));
         if (!ls.pdf.delta) {
             if (ls.pdf.value > 0.0) {
@@ -815,7 +798,7 @@ __global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(cons
 
     // BSDF sample (:167-195)
     SurfaceSample ss;
-    if (!material_sample(s, material, vs, w_o, normal, tu, tv, ss, bad)) { finish(L, shadow_pending); return; }
+    if (!material_sample<LOBES>(s, material, vs, w_o, normal, tu, tv, ss, bad)) { finish(L, shadow_pending); return; }
     if (is_black(ss.f)) { finish(L, shadow_pending); return; }
     const double cos_theta = fabs(dot(ss.w_i, normal));
     const double bsdf_pdf = ss.pdf.delta ? 1.0 : ss.pdf.value;
@@ -845,6 +828,66 @@ __global__ void __launch_bounds__(kShadeThreads, CRAY_SHADE_BLOCKS) k_shade(cons
                      (contact ? kStateContact : 0u);
     } else {
         p.state[i] = SLOT_DONE | (next_bounces << 8) | ((shadow_pending ? 1u : 0u) << 17) | ((bad ? 1u : 0u) << 18);
+    }
+}
+
+// Resident CTAs per SM the register allocation of each class kernel is held to (3 = 80 registers: measured against 2, 4 and 6 --
+// shade 24.5 ms per 256-spp dragon frame against 25.1, 26.5 and 29.4; the spills of the 64-register build cost more than its occupancy gains)
+#ifndef CRAY_SHADE_BLOCKS_MATTE
+#define CRAY_SHADE_BLOCKS_MATTE 3
+#endif
+#ifndef CRAY_SHADE_BLOCKS_GLASS
+#define CRAY_SHADE_BLOCKS_GLASS 3
+#endif
+#ifndef CRAY_SHADE_BLOCKS_PLASTIC
+#define CRAY_SHADE_BLOCKS_PLASTIC 3
+#endif
+#ifndef CRAY_SHADE_BLOCKS_METAL
+#define CRAY_SHADE_BLOCKS_METAL 3
+#endif
+__host__ __device__ constexpr int shade_blocks_of_class(uint32_t cls) {
+    return cls == CRAY_MAT_MATTE ? CRAY_SHADE_BLOCKS_MATTE : cls == CRAY_MAT_GLASS ? CRAY_SHADE_BLOCKS_GLASS : cls == CRAY_MAT_PLASTIC ? CRAY_SHADE_BLOCKS_PLASTIC : CRAY_SHADE_BLOCKS_METAL;
+}
+
+template <uint32_t CLS>
+__global__ void __launch_bounds__(kShadeThreads, shade_blocks_of_class(CLS)) k_shade_class(const __grid_constant__ SceneView s, const __grid_constant__ Pool p, const __grid_constant__ Job job, Counters* counters) {
+    // the three shape queues of this class, walked as one range
+    const uint64_t n0 = counters->class_count[CLS * 3u], n1 = counters->class_count[CLS * 3u + 1u], n2 = counters->class_count[CLS * 3u + 2u];
+    const uint64_t n = n0 + n1 + n2;
+    for (uint64_t t = (uint64_t)blockIdx.x * kShadeThreads + threadIdx.x; t < n; t += (uint64_t)gridDim.x * kShadeThreads) {
+        const uint32_t shape = t < n0 ? 0u : (t < n0 + n1 ? 1u : 2u);
+        const uint64_t local = t - (shape == 0u ? 0ull : (shape == 1u ? n0 : n0 + n1));
+        const uint32_t i = p.class_queue[(uint64_t)(CLS * 3u + shape) * p.capacity + local];
+        shade_vertex<CLS>(s, p, job, counters, i, p.hit_slot[i]);
+    }
+}
+
+// The paths that left the scene (path_integrator.rs:60-90).
+__global__ void __launch_bounds__(kShadeThreads) k_shade_miss(const __grid_constant__ SceneView s, const __grid_constant__ Pool p, Counters* counters) {
+    const uint64_t n = counters->class_count[kKeyMiss];
+    for (uint64_t t = (uint64_t)blockIdx.x * kShadeThreads + threadIdx.x; t < n; t += (uint64_t)gridDim.x * kShadeThreads) {
+        const uint32_t i = p.class_queue[(uint64_t)kKeyMiss * p.capacity + t];
+        const uint32_t st = p.state[i];
+        const uint32_t bounces = st_bounces(st);
+        const bool is_specular_bounce = (st >> 16) & 1u;
+        const bool bad = (st >> 18) & 1u;
+        Color3 L = mkc(p.L_r[i], p.L_g[i], p.L_b[i]);
+        const Color3 beta = mkc(p.beta_r[i], p.beta_g[i], p.beta_b[i]);
+        const double prev_bsdf_pdf = p.prev_bsdf_pdf[i];
+        for (uint32_t li = 0; li < s.n_lights; ++li) {
+            const DevLight& light = s.lights[li];
+            if (light.kind != CRAY_LIGHT_INFINITE) continue;  // Light::Le is black for every other kind (light.rs:161-168)
+            const Color3 Le = mkc(light.color[0], light.color[1], light.color[2]);
+            if (is_specular_bounce) {
+                L = L + beta * Le;
+            } else if (!is_black(Le)) {
+                const double light_pdf = (kFrac1Pi / 4.0) * light_pick_pdf(s, li);
+                const double weight = power_heuristic(light_pdf, prev_bsdf_pdf);
+                L = L + beta * Le * weight;
+            }
+        }
+        p.L_r[i] = L.r; p.L_g[i] = L.g; p.L_b[i] = L.b;
+        p.state[i] = SLOT_DONE | (bounces << 8) | ((bad ? 1u : 0u) << 18);
     }
 }
 
@@ -879,6 +922,7 @@ struct PoolStorage {
     WideTuning tune{12, 8};
     unsigned shadow_blocks = 0;       // the any-hit instantiation needs fewer registers: its own occupancy
     unsigned f32_blocks = 0, f32_shadow_blocks = 0;  // F32 mode instantiations
+    unsigned shade_blocks = 0;        // grid of the per-class shade kernels (grid-stride loops over their queues)
     unsigned long long* d_trace_counters = nullptr;  // {n, cursor, n of the reference-order launch} for the S3 entry points
     uint32_t* d_trace_list = nullptr;                // S3 ray lists of k_classify_rays (grow only)
     uint64_t trace_list_capacity = 0;
@@ -930,12 +974,13 @@ int ensure_pool(cray_scene* sc, uint32_t capacity) {
         if (const char* e = std::getenv("CRAY_REFILL_LANES")) ps->tune.refill_lanes = std::max(1, std::min(32, std::atoi(e)));
         if (const char* e = std::getenv("CRAY_WAIT_LANES")) ps->tune.wait_lanes = std::max(1, std::min(33, std::atoi(e)));
         if (const char* e = std::getenv("CRAY_BLOCKS_PER_SM")) ps->persistent_blocks = ps->shadow_blocks = ps->f32_blocks = ps->f32_shadow_blocks = (unsigned)(sms * std::max(1, std::atoi(e)));
+        ps->shade_blocks = (unsigned)(sms * 16);
         ps->initialised = true;
     }
     if (ps->pool.capacity >= capacity) return CRAY_OK;
     if (ps->slab) { cudaDeviceSynchronize(); cudaFree(ps->slab); ps->slab = nullptr; }  // (re-)allocation is rare: grow only
     const size_t n = capacity;
-    const size_t n_f64 = 21, n_u32 = 8;
+    const size_t n_f64 = 21, n_u32 = 8 + 13;  // (+ the 13 queues of the shade stage)
     const size_t bytes = n * (n_f64 * 8 + n_u32 * 4);
     CRAY_CUDA(cudaMalloc(&ps->slab, bytes));
     // cleared before anyone can touch it, whichever stream the caller renders on
@@ -951,6 +996,7 @@ int ensure_pool(cray_scene* sc, uint32_t capacity) {
     uint32_t** ufields[] = {&p.hit_slot, &p.id, &p.pixel, &p.hash, &p.shuffled_rev, &p.state, &p.extend_queue, &p.shadow_queue};
     k = 0;
     for (uint32_t** up : ufields) { *up = u + k * n; ++k; }
+    p.class_queue = u + k * n;
     p.capacity = capacity;
     return CRAY_OK;
 }
@@ -1002,7 +1048,16 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
         else k_wide_persistent<false, ExtendSource><<<gp, 128, 0, stream>>>(sc->view, ExtendSource{pool}, &dc->n_extend, &dc->extend_cursor, ps->tune);
         if (contact) k_extend_exact<true><<<gx, 128, 0, stream>>>(sc->view, pool, &dc->n_extend_contact);
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 2], stream));
-        k_shade<<<(capacity + kShadeThreads - 1) / kShadeThreads, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
+        {
+            const unsigned blocks = (capacity + kShadeThreads - 1) / kShadeThreads;
+            const unsigned strided = std::min(blocks, ps->shade_blocks);   // the class kernels walk their queues with a grid stride
+            k_shade_classify<<<blocks, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
+            k_shade_class<CRAY_MAT_METAL><<<strided, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
+            k_shade_class<CRAY_MAT_MATTE><<<strided, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
+            k_shade_class<CRAY_MAT_PLASTIC><<<strided, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
+            k_shade_class<CRAY_MAT_GLASS><<<strided, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
+            k_shade_miss<<<strided, kShadeThreads, 0, stream>>>(sc->view, pool, dc);
+        }
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 3], stream));
         // at most one shadow ray per shaded vertex; the queue lengths live on the device
         if (job.exact) k_shadow_exact<false><<<gx, 128, 0, stream>>>(sc->view, pool, &dc->n_shadow);
@@ -1012,7 +1067,7 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
         else k_wide_persistent<true, ShadowSource><<<gs, 128, 0, stream>>>(sc->view, ShadowSource{pool}, &dc->n_shadow, &dc->shadow_cursor, ps->tune);
         if (contact) k_shadow_exact<true><<<gx, 128, 0, stream>>>(sc->view, pool, &dc->n_shadow_contact);
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 4], stream));
-        launches += contact ? 7 : 5;
+        launches += contact ? 12 : 10;
         CRAY_CUDA(cudaEventSynchronize(ev.gen_done));
         const uint64_t live = ps->h_counters->n_extend + ps->h_counters->n_extend_contact;
         if (live == 0) break;

@@ -10,7 +10,7 @@ python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_$TAG.log 2>&1
 SHORT="python bench.py --spp 256 --steps 1 --warmup 1 --no-cpu-baseline --no-f32-leg"
 $SHORT > $O/plain_$TAG.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 420 --csv --log-file $O/launches_$TAG.csv $SHORT > $O/ncu_a_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'k_generate|k_wide_persistent|k_shade' -s 12 -c 4 -o $O/prof_$TAG $SHORT > $O/ncu_b_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_generate|k_wide_persistent|k_shade' -s 27 -c 9 -o $O/prof_$TAG $SHORT > $O/ncu_b_$TAG.log 2>&1
 $SHORT --mode f32 > $O/plain_${TAG}_f32.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'k_wide_persistent' -s 6 -c 1 -o $O/prof_${TAG}_f32 $SHORT --mode f32 > $O/ncu_c_$TAG.log 2>&1
 tail -c 600 $O/bench_$TAG.json; echo; cat $O/smoke_$TAG.log | tail -2; tail -2 $O/ncu_b_$TAG.log; tail -2 $O/ncu_c_$TAG.log
