@@ -130,6 +130,7 @@ struct Component {
 struct Decoder {
     const uint8_t* data;
     size_t n;
+    Decoder(const uint8_t* bytes, size_t size) : data(bytes), n(size) {}
     size_t pos = 0;
     uint16_t quant[4][64] = {};
     bool quant_present[4] = {};
@@ -783,7 +784,7 @@ void png_run(const uint8_t* data, size_t n, uint32_t& w, uint32_t& h, std::vecto
 
 bool decode_jpeg(const uint8_t* data, size_t n, uint32_t& width, uint32_t& height, std::vector<uint8_t>& rgb, std::string& err) {
     try {
-        Decoder d{data, n};
+        Decoder d(data, n);
         d.run(width, height, rgb);
         return true;
     } catch (const JpegError& e) {

@@ -593,6 +593,8 @@ __global__ void k_begin_iteration(Counters* c) {
     c->shadow_traced += c->n_shadow + c->n_shadow_contact;
     c->contact_rays += c->n_extend_contact + c->n_shadow_contact;
     c->n_extend = 0; c->n_shadow = 0; c->extend_cursor = 0; c->shadow_cursor = 0; c->n_extend_contact = 0; c->n_shadow_contact = 0;
+    // every vertex on a surface makes the reference's Scene::intersects call (path_integrator.rs:141): one counted shadow ray each
+    for (uint32_t k = 0; k < 12u; ++k) c->shadow_rays += c->class_count[k];
     for (int k = 0; k < 16; ++k) c->class_count[k] = 0;
 }
 
@@ -758,8 +760,7 @@ __device__ __forceinline__ void shade_vertex(const SceneView& s, const Pool& p, 
     // next-event estimation (:129-164): the shadow ray is traced by the shadow stage, the contribution is parked.
     // Where every lobe of the material is perfectly specular, Material::f is black for every direction, so the light sample
     // cannot contribute: it is not drawn (the reference's shadow ray, :141, is still counted).
-    bool shadow_pending = false;
-    warp_count(&counters->shadow_rays, true);
+    bool shadow_pending = false;   // (the reference's shadow ray of this vertex is counted from the queue lengths, k_begin_iteration)
     // Both rays of this vertex start at `location`.  If it lies in the outer shell of a marked node box, only the reference-order
     // traversal reproduces what the reference's box test does to them (bvh_build.hpp "planar contact"); directions are unit vectors.
     const bool contact = !job.exact && (lp.kind & kKindContact) && origin_in_contact_shell(s, location, kContactTol);
@@ -803,7 +804,8 @@ __device__ __forceinline__ void shade_vertex(const SceneView& s, const Pool& p, 
     const double cos_theta = fabs(dot(ss.w_i, normal));
     const double bsdf_pdf = ss.pdf.delta ? 1.0 : ss.pdf.value;
     if (bsdf_pdf == 0.0) { finish(L, shadow_pending); return; }
-    beta = beta * ss.f * cos_theta / bsdf_pdf;
+    beta = beta * ss.f * cos_theta;
+    if (bsdf_pdf != 1.0) beta = beta / bsdf_pdf;   // (x / 1.0 is x, bit for bit: perfectly specular lobes skip three divisions)
 
     // Russian roulette (:197-206)
     if (bounces > 0) {
