@@ -50,7 +50,10 @@ struct RefBvh {
 Box3 primitive_bounds(const cray_scene_desc& d, uint64_t prim);
 void build_reference_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads = 0);
 
-struct alignas(16) WideNode {  // 80 B: five 16-byte loads
+#ifndef CRAY_NODE96
+#define CRAY_NODE96 0   // 1 (tuning): nodes padded to 96 bytes on 32-byte boundaries, fetched with three 256-bit loads
+#endif
+struct alignas(CRAY_NODE96 ? 32 : 16) WideNode {  // 80 B: five 16-byte loads
     float px, py, pz;          // quantisation frame origin
     uint8_t ex, ey, ez;        // per-axis scale = 2^(e - 127) (raw f32 exponent field)
     uint8_t imask;             // bit s: slot s holds an interior child
@@ -61,7 +64,7 @@ struct alignas(16) WideNode {  // 80 B: five 16-byte loads
     uint8_t qlo[3][8];         // quantised child box minima  [axis][slot]
     uint8_t qhi[3][8];         // quantised child box maxima
 };
-static_assert(sizeof(WideNode) == 80, "WideNode layout");
+static_assert(sizeof(WideNode) == (CRAY_NODE96 ? 96 : 80), "WideNode layout");
 
 constexpr int kWideStackLimit = 24;  // traversal stack entries per ray (traverse.cuh): one per level
 

@@ -234,9 +234,19 @@ __device__ __forceinline__ uint32_t pop_child(uint2& g, uint32_t octinv) {
 }
 
 __device__ __forceinline__ NodeData load_node(const SceneView& s, uint32_t index) {
-    const int4* raw = reinterpret_cast<const int4*>(s.wide_nodes + index);
     NodeData n;
+#if CRAY_NODE96
+    // sm_100: 256-bit global loads (LDG.E.ENL2.256), three per 96-byte node instead of five 128-bit ones per 80-byte node
+    const char* raw = reinterpret_cast<const char*>(s.wide_nodes + index);
+    int4 pad;
+    asm("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(n.n0.x), "=r"(n.n0.y), "=r"(n.n0.z), "=r"(n.n0.w), "=r"(n.n1.x), "=r"(n.n1.y), "=r"(n.n1.z), "=r"(n.n1.w) : "l"(raw));
+    asm("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(n.n2.x), "=r"(n.n2.y), "=r"(n.n2.z), "=r"(n.n2.w), "=r"(n.n3.x), "=r"(n.n3.y), "=r"(n.n3.z), "=r"(n.n3.w) : "l"(raw + 32));
+    asm("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(n.n4.x), "=r"(n.n4.y), "=r"(n.n4.z), "=r"(n.n4.w), "=r"(pad.x), "=r"(pad.y), "=r"(pad.z), "=r"(pad.w) : "l"(raw + 64));
+    (void)pad;
+#else
+    const int4* raw = reinterpret_cast<const int4*>(s.wide_nodes + index);
     n.n0 = __ldg(raw); n.n1 = __ldg(raw + 1); n.n2 = __ldg(raw + 2); n.n3 = __ldg(raw + 3); n.n4 = __ldg(raw + 4);
+#endif
     return n;
 }
 

@@ -1322,7 +1322,9 @@ int cray_render_device(cray_scene* sc, int mode, uint64_t seed, uint32_t sample_
         job.sobol = sc->d_sobol;
         job.exact = mode == CRAY_TRAVERSE_EXACT;
         job.f32 = mode == CRAY_TRAVERSE_F32;
-        uint32_t pool_log2 = 23;  // path slots in flight (1.7 GB of path state); CRAY_POOL_LOG2 overrides it for tuning
+        // path slots in flight: up to 2^26 (17 GB of path state and queues of the 180 GB; measured 2^22 .. 2^26, profiles/r2d_pool_sweep.txt:
+        // longer launches amortise the tails of the persistent traversal kernels); CRAY_POOL_LOG2 overrides it for tuning
+        uint32_t pool_log2 = 26;
         if (const char* e = std::getenv("CRAY_POOL_LOG2")) pool_log2 = (uint32_t)std::max(10, std::min(26, std::atoi(e)));
         const uint32_t capacity = (uint32_t)std::min<uint64_t>(n_total, 1ull << pool_log2);
         rc = run_wavefront(sc, job, capacity, stream, stats);
