@@ -73,6 +73,8 @@ struct Builder {
     size_t grain;                 // subtrees at or below this size are deferred to the pool (0 = never defer)
     std::vector<Task>* tasks;
     unsigned threads = 1;         // > 1: the passes over the items of a large node run on this many threads
+    bool all_axes = false;        // false: the reference's rule (split along the longest centroid axis, bvh.rs:253); true: the cheapest
+                                  // of the three axes' best splits (build_quality_bvh: the tree the wide BVH is collapsed from)
 
     uint32_t leaf(SubTree& t, const Item* items, size_t n, const Box3& box) {
         uint32_t idx = (uint32_t)t.nodes.size();
@@ -122,8 +124,8 @@ struct Builder {
             return leaf(t, items, n, bounds);
         }
         const Box3 cb = cent.box();
-        const int axis = box_maximum_extent(cb);
-        const double cmin = cb.lo[axis], cext = cb.hi[axis] - cb.lo[axis];
+        int axis = box_maximum_extent(cb);
+        double cmin = cb.lo[axis], cext = cb.hi[axis] - cb.lo[axis];
 
         struct Buckets {
             Accum box[kBuckets];
@@ -140,40 +142,66 @@ struct Builder {
                 dst.count[b] += 1;
             }
         };
-        if (parallel) {
-            std::vector<Buckets> part(threads);
-            parallel_chunks(n, threads, [&](unsigned c, size_t b0, size_t e0) {
-                Buckets local;
-                fill(local, b0, e0);
-                part[c] = local;
-            });
-            for (unsigned c = 0; c < threads; ++c)
-                for (uint32_t b = 0; b < kBuckets; ++b) {
-                    if (part[c].box[b].some) bk.box[b].add(part[c].box[b].lo, part[c].box[b].hi);
-                    bk.count[b] += part[c].count[b];
-                }
-        } else {
-            fill(bk, 0, n);
-        }
-        Accum* bucket_box = bk.box;
-        size_t* bucket_count = bk.count;
-        double costs[kBuckets - 1];
-        for (uint32_t i = 0; i + 1 < kBuckets; ++i) {
-            double cost = kTraversalCost;
-            for (int part = 0; part < 2; ++part) {
-                const uint32_t lo = part == 0 ? 0 : i + 1, hi = part == 0 ? i + 1 : kBuckets;
-                Accum merged;
-                size_t count = 0;
-                for (uint32_t k = lo; k < hi; ++k)
-                    if (bucket_box[k].some) { merged.add(bucket_box[k].lo, bucket_box[k].hi); count += bucket_count[k]; }
-                if (merged.some) cost += (double)count * box_surface_area(merged.box()) / total_surface_area;
+        auto fill_all = [&]() {
+            bk = Buckets{};
+            if (parallel) {
+                std::vector<Buckets> part(threads);
+                parallel_chunks(n, threads, [&](unsigned c, size_t b0, size_t e0) {
+                    Buckets local;
+                    fill(local, b0, e0);
+                    part[c] = local;
+                });
+                for (unsigned c = 0; c < threads; ++c)
+                    for (uint32_t b = 0; b < kBuckets; ++b) {
+                        if (part[c].box[b].some) bk.box[b].add(part[c].box[b].lo, part[c].box[b].hi);
+                        bk.count[b] += part[c].count[b];
+                    }
+            } else {
+                fill(bk, 0, n);
             }
-            if (!std::isfinite(cost) && t.error.empty()) t.error = "SAH cost is not finite";
-            costs[i] = cost;
-        }
+        };
+        double costs[kBuckets - 1];
         uint32_t best = 0;
-        for (uint32_t i = 0; i + 1 < kBuckets; ++i)
-            if (costs[i] < costs[best]) best = i;
+        auto evaluate = [&]() {
+            Accum* bucket_box = bk.box;
+            size_t* bucket_count = bk.count;
+            for (uint32_t i = 0; i + 1 < kBuckets; ++i) {
+                double cost = kTraversalCost;
+                for (int part = 0; part < 2; ++part) {
+                    const uint32_t lo = part == 0 ? 0 : i + 1, hi = part == 0 ? i + 1 : kBuckets;
+                    Accum merged;
+                    size_t count = 0;
+                    for (uint32_t k = lo; k < hi; ++k)
+                        if (bucket_box[k].some) { merged.add(bucket_box[k].lo, bucket_box[k].hi); count += bucket_count[k]; }
+                    if (merged.some) cost += (double)count * box_surface_area(merged.box()) / total_surface_area;
+                }
+                if (!std::isfinite(cost) && t.error.empty()) t.error = "SAH cost is not finite";
+                costs[i] = cost;
+            }
+            best = 0;
+            for (uint32_t i = 0; i + 1 < kBuckets; ++i)
+                if (costs[i] < costs[best]) best = i;
+        };
+        if (all_axes) {
+            // the cheapest split over the three axes (an axis along which every centroid coincides cannot split)
+            int best_axis = -1;
+            double best_cost = 0.0;
+            for (int a = 0; a < 3; ++a) {
+                if (!(cb.hi[a] - cb.lo[a] > 0.0)) continue;
+                axis = a; cmin = cb.lo[a]; cext = cb.hi[a] - cb.lo[a];
+                fill_all();
+                evaluate();
+                size_t left = 0;
+                for (uint32_t b = 0; b <= best; ++b) left += bk.count[b];
+                if (left == 0 || left == n) continue;
+                if (best_axis < 0 || costs[best] < best_cost) { best_axis = a; best_cost = costs[best]; }
+            }
+            axis = best_axis < 0 ? box_maximum_extent(cb) : best_axis;
+            cmin = cb.lo[axis]; cext = cb.hi[axis] - cb.lo[axis];
+        }
+        fill_all();
+        evaluate();
+        size_t* bucket_count = bk.count;
 
         if ((double)n <= costs[best] && n <= kMaxLeaf) return leaf(t, items, n, bounds);
 
@@ -313,7 +341,13 @@ Box3 primitive_bounds(const cray_scene_desc& d, uint64_t prim) {  // Shape::boun
     }
 }
 
-void build_reference_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads) {
+namespace {
+void build_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads, bool all_axes);
+}
+void build_reference_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads) { build_bvh(d, out, threads, false); }
+void build_quality_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads) { build_bvh(d, out, threads, true); }
+namespace {
+void build_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads, bool all_axes) {
     PhaseTimer timer;
     const size_t n = (size_t)d.n_primitives;
     out = RefBvh{};
@@ -345,13 +379,13 @@ void build_reference_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads
 
     std::vector<Task> tasks;
     SubTree top;
-    Builder top_builder{(threads > 1 && n > (1u << 16)) ? std::max<size_t>(1u << 15, n / (threads * 8)) : 0, &tasks, threads};
+    Builder top_builder{(threads > 1 && n > (1u << 16)) ? std::max<size_t>(1u << 15, n / (threads * 8)) : 0, &tasks, threads, all_axes};
     top_builder.split(top, items.data(), n);
     timer.mark("top of the tree");
     if (!tasks.empty()) {
         std::atomic<size_t> next{0};
         auto run = [&]() {
-            Builder b{0, nullptr, 1};
+            Builder b{0, nullptr, 1, all_axes};
             for (;;) {
                 size_t i = next.fetch_add(1);
                 if (i >= tasks.size()) break;
@@ -372,6 +406,7 @@ void build_reference_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads
     splice(top, tasks, out);
     timer.mark("splice");
 }
+}  // namespace
 
 // ---- planar contact analysis (see bvh_build.hpp) ------------------------------------------------------------------------
 

@@ -49,6 +49,10 @@ struct RefBvh {
 // Bounds of primitive i exactly as Shape::bounds computes them (src/shape.rs:402-438).
 Box3 primitive_bounds(const cray_scene_desc& d, uint64_t prim);
 void build_reference_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads = 0);
+// The same builder choosing, at every node, the cheapest of the three axes' best binned splits instead of the reference's
+// longest-centroid-axis rule: the tree the 8-wide BVH can be collapsed from (hits do not depend on it: the f64 leaf tests decide,
+// and exact-t ties are resolved on the reference tree).
+void build_quality_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads = 0);
 
 #ifndef CRAY_NODE96
 #define CRAY_NODE96 0   // 1 (tuning): nodes padded to 96 bytes on 32-byte boundaries, fetched with three 256-bit loads

@@ -219,7 +219,16 @@ int build_host_side(const cray_scene_desc* d, uint32_t build_flags, HostBuild& h
     build_reference_bvh(*d, ref);
     if (!ref.error.empty()) { set_error(ref.error); return CRAY_E_BVH; }
     if (build_flags & CRAY_BUILD_FAST) {
-        collapse_to_wide(*d, ref, wide);
+        // CRAY_WIDE_TREE=sah3 (tuning): collapse the wide BVH from a second tree built with three-axis SAH splits
+        const char* tree = std::getenv("CRAY_WIDE_TREE");
+        if (tree && std::string(tree) == "sah3") {
+            RefBvh quality;
+            build_quality_bvh(*d, quality);
+            if (!quality.error.empty()) { set_error(quality.error); return CRAY_E_BVH; }
+            collapse_to_wide(*d, quality, wide);
+        } else {
+            collapse_to_wide(*d, ref, wide);
+        }
         if (wide.depth >= (uint32_t)kWideStackLimit) { set_error("wide BVH deeper than the traversal stack"); return CRAY_E_BVH; }
         if (d->n_primitives >= (1ull << 27)) { set_error("more than 2^27 primitives: the fast traversal's queue entries hold 27-bit leaf slots"); return CRAY_E_UNSUPPORTED; }
     }

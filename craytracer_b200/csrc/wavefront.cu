@@ -83,6 +83,23 @@ struct Counters {
 __device__ __forceinline__ uint32_t st_state(uint32_t s) { return s & 0xFFu; }
 __device__ __forceinline__ uint32_t st_bounces(uint32_t s) { return (s >> 8) & 0xFFu; }
 
+// A finished path goes into the film where it ends (craytracer.rs:177-188 accumulates the sample into its pixel) -- in the shade
+// kernel that ended it or, if its last light sample is still being tested, in the shadow kernel -- and frees its slot.  A sample on
+// which the reference would have panicked (path_integrator.rs:208-209 and the asserts of its callees) is dropped and counted.
+__device__ __forceinline__ void flush_path(const Pool& p, const Job& job, Counters* counters, uint32_t i, double r, double g, double b, bool bad) {
+    if (bad || !(isfinite(r) && isfinite(g) && isfinite(b))) {
+        atomicAdd(&counters->nan_samples, 1ull);
+    } else if (job.film) {
+        double* px = job.film + 3ull * p.pixel[i];
+        atomicAdd(px, r); atomicAdd(px + 1, g); atomicAdd(px + 2, b);
+    }
+    if (job.out_rgb) {
+        double* dst = job.out_rgb + 3ull * p.id[i];
+        dst[0] = r; dst[1] = g; dst[2] = b;
+    }
+    p.state[i] = SLOT_EMPTY;
+}
+
 // ---- ray sources for the persistent wide-BVH kernel -------------------------------------------------------------
 
 struct ExtendSource {  // queued path rays -> Pool::hit_*
@@ -104,8 +121,23 @@ struct ExtendSource {  // queued path rays -> Pool::hit_*
     __device__ __forceinline__ void store_any(uint32_t, bool) const {}
 };
 
+// The result of a path's shadow ray: the parked contribution is added when unoccluded; a path that had already ended (its state
+// waited for this) is flushed.
+__device__ __forceinline__ void settle_shadow(const Pool& p, const Job& job, Counters* counters, uint32_t i, bool occluded) {
+    const uint32_t st = p.state[i];
+    if (st_state(st) == SLOT_DONE) {
+        double r = p.L_r[i], g = p.L_g[i], b = p.L_b[i];
+        if (!occluded) { r += p.sc_r[i]; g += p.sc_g[i]; b += p.sc_b[i]; }
+        flush_path(p, job, counters, i, r, g, b, (st >> 18) & 1u);
+    } else if (!occluded) {
+        p.L_r[i] += p.sc_r[i]; p.L_g[i] += p.sc_g[i]; p.L_b[i] += p.sc_b[i];
+    }
+}
+
 struct ShadowSource {  // queued shadow rays -> L += contribution when unoccluded (path_integrator.rs:141-163)
     Pool p;
+    Job job;
+    Counters* counters;
     __device__ __forceinline__ uint32_t load(uint64_t idx, V3& o, V3& d, double& ray_max) const {
         const uint32_t i = p.shadow_queue[idx];
         o = mk(p.ox[i], p.oy[i], p.oz[i]);
@@ -114,9 +146,7 @@ struct ShadowSource {  // queued shadow rays -> L += contribution when unocclude
         return i;
     }
     __device__ __forceinline__ void store_closest(const SceneView&, uint32_t, uint32_t, double) const {}
-    __device__ __forceinline__ void store_any(uint32_t i, bool occluded) const {
-        if (!occluded) { p.L_r[i] += p.sc_r[i]; p.L_g[i] += p.sc_g[i]; p.L_b[i] += p.sc_b[i]; }
-    }
+    __device__ __forceinline__ void store_any(uint32_t i, bool occluded) const { settle_shadow(p, job, counters, i, occluded); }
 };
 
 // `h.u, h.v` are only consulted when `have_uv`; otherwise a triangle's barycentrics are re-derived from (slot, t).
@@ -709,9 +739,11 @@ __device__ __forceinline__ void shade_vertex(const SceneView& s, const Pool& p, 
     Color3 beta = mkc(p.beta_r[i], p.beta_g[i], p.beta_b[i]);
     const double prev_bsdf_pdf = p.prev_bsdf_pdf[i];
 
+    // the path ends here: into the film right away, unless its light sample is still to be tested (then the shadow kernel flushes)
     auto finish = [&](Color3 Lf, bool shadow_pending) {
+        if (!shadow_pending) { flush_path(p, job, counters, i, Lf.r, Lf.g, Lf.b, bad); return; }
         p.L_r[i] = Lf.r; p.L_g[i] = Lf.g; p.L_b[i] = Lf.b;
-        p.state[i] = SLOT_DONE | (bounces << 8) | ((shadow_pending ? 1u : 0u) << 17) | ((bad ? 1u : 0u) << 18);
+        p.state[i] = SLOT_DONE | (bounces << 8) | (1u << 17) | ((bad ? 1u : 0u) << 18);
     };
 
     const LeafPrim lp = load_leaf_prim((job.exact ? s.bin_prims : s.wide_prims) + slot);
@@ -821,15 +853,18 @@ __device__ __forceinline__ void shade_vertex(const SceneView& s, const Pool& p, 
     if (!is_finite3(L) || !is_finite3(beta)) { bad = true; finish(L, shadow_pending); return; }
 
     const uint32_t next_bounces = bounces + 1;
-    p.L_r[i] = L.r; p.L_g[i] = L.g; p.L_b[i] = L.b;
     if (next_bounces < s.max_depth && !is_black(beta)) {  // loop condition (:54)
+        p.L_r[i] = L.r; p.L_g[i] = L.g; p.L_b[i] = L.b;
         p.dx[i] = ss.w_i.x; p.dy[i] = ss.w_i.y; p.dz[i] = ss.w_i.z;
         p.beta_r[i] = beta.r; p.beta_g[i] = beta.g; p.beta_b[i] = beta.b;
         p.prev_bsdf_pdf[i] = bsdf_pdf;
         p.state[i] = SLOT_ACTIVE | (next_bounces << 8) | ((ss.is_specular ? 1u : 0u) << 16) | ((shadow_pending ? 1u : 0u) << 17) | ((bad ? 1u : 0u) << 18) |
                      (contact ? kStateContact : 0u);
+    } else if (shadow_pending) {
+        p.L_r[i] = L.r; p.L_g[i] = L.g; p.L_b[i] = L.b;
+        p.state[i] = SLOT_DONE | (next_bounces << 8) | (1u << 17) | ((bad ? 1u : 0u) << 18);
     } else {
-        p.state[i] = SLOT_DONE | (next_bounces << 8) | ((shadow_pending ? 1u : 0u) << 17) | ((bad ? 1u : 0u) << 18);
+        flush_path(p, job, counters, i, L.r, L.g, L.b, bad);
     }
 }
 
@@ -865,12 +900,11 @@ __global__ void __launch_bounds__(kShadeThreads, shade_blocks_of_class(CLS)) k_s
 }
 
 // The paths that left the scene (path_integrator.rs:60-90).
-__global__ void __launch_bounds__(kShadeThreads) k_shade_miss(const __grid_constant__ SceneView s, const __grid_constant__ Pool p, Counters* counters) {
+__global__ void __launch_bounds__(kShadeThreads) k_shade_miss(const __grid_constant__ SceneView s, const __grid_constant__ Pool p, const __grid_constant__ Job job, Counters* counters) {
     const uint64_t n = counters->class_count[kKeyMiss];
     for (uint64_t t = (uint64_t)blockIdx.x * kShadeThreads + threadIdx.x; t < n; t += (uint64_t)gridDim.x * kShadeThreads) {
         const uint32_t i = p.class_queue[(uint64_t)kKeyMiss * p.capacity + t];
         const uint32_t st = p.state[i];
-        const uint32_t bounces = st_bounces(st);
         const bool is_specular_bounce = (st >> 16) & 1u;
         const bool bad = (st >> 18) & 1u;
         Color3 L = mkc(p.L_r[i], p.L_g[i], p.L_b[i]);
@@ -888,20 +922,18 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_miss(const __grid_const
                 L = L + beta * Le * weight;
             }
         }
-        p.L_r[i] = L.r; p.L_g[i] = L.g; p.L_b[i] = L.b;
-        p.state[i] = SLOT_DONE | (bounces << 8) | ((bad ? 1u : 0u) << 18);
+        flush_path(p, job, counters, i, L.r, L.g, L.b, bad);
     }
 }
 
 template <bool BACK>
-__global__ void __launch_bounds__(128) k_shadow_exact(SceneView s, Pool p, const unsigned long long* __restrict__ n_ptr) {
+__global__ void __launch_bounds__(128) k_shadow_exact(SceneView s, Pool p, Job job, Counters* counters, const unsigned long long* __restrict__ n_ptr) {
     const uint64_t n = *n_ptr;
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t i = p.shadow_queue[BACK ? p.capacity - 1u - (uint32_t)q : (uint32_t)q];
         Hit h;
-        if (!traverse_exact<true>(s, mk(p.ox[i], p.oy[i], p.oz[i]), mk(p.sdx[i], p.sdy[i], p.sdz[i]), p.smax[i], h)) {
-            p.L_r[i] += p.sc_r[i]; p.L_g[i] += p.sc_g[i]; p.L_b[i] += p.sc_b[i];
-        }
+        const bool occluded = traverse_exact<true>(s, mk(p.ox[i], p.oy[i], p.oz[i]), mk(p.sdx[i], p.sdy[i], p.sdz[i]), p.smax[i], h);
+        settle_shadow(p, job, counters, i, occluded);
     }
 }
 
@@ -1058,16 +1090,16 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
             k_shade_class<CRAY_MAT_MATTE><<<strided, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
             k_shade_class<CRAY_MAT_PLASTIC><<<strided, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
             k_shade_class<CRAY_MAT_GLASS><<<strided, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
-            k_shade_miss<<<strided, kShadeThreads, 0, stream>>>(sc->view, pool, dc);
+            k_shade_miss<<<strided, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
         }
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 3], stream));
         // at most one shadow ray per shaded vertex; the queue lengths live on the device
-        if (job.exact) k_shadow_exact<false><<<gx, 128, 0, stream>>>(sc->view, pool, &dc->n_shadow);
+        if (job.exact) k_shadow_exact<false><<<gx, 128, 0, stream>>>(sc->view, pool, job, dc, &dc->n_shadow);
         // (F32 mode traces its shadow rays with the f64 any-hit kernel: measured faster than the f32 one, 20.9 against 24.0 ms per
         // 256-spp dragon frame -- the f32 instantiation's larger shared-memory footprint leaves it less L1 -- and exact at the
         // light's end of the ray.  The f32 any-hit kernel serves cray_trace_any.)
-        else k_wide_persistent<true, ShadowSource><<<gs, 128, 0, stream>>>(sc->view, ShadowSource{pool}, &dc->n_shadow, &dc->shadow_cursor, ps->tune);
-        if (contact) k_shadow_exact<true><<<gx, 128, 0, stream>>>(sc->view, pool, &dc->n_shadow_contact);
+        else k_wide_persistent<true, ShadowSource><<<gs, 128, 0, stream>>>(sc->view, ShadowSource{pool, job, dc}, &dc->n_shadow, &dc->shadow_cursor, ps->tune);
+        if (contact) k_shadow_exact<true><<<gx, 128, 0, stream>>>(sc->view, pool, job, dc, &dc->n_shadow_contact);
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 4], stream));
         launches += contact ? 12 : 10;
         CRAY_CUDA(cudaEventSynchronize(ev.gen_done));
