@@ -264,50 +264,63 @@ struct Builder {
     }
 };
 
-// Splice `src` (local indices / ranks) into the final pre-order arrays.
-void splice(const SubTree& src, const std::vector<Task>& tasks, RefBvh& out) {
-    // iterative DFS over src in pre-order; deferred placeholders expand recursively
+// Splice `src` (local indices / ranks) into the final pre-order arrays: one depth-first pass over the (small) top of the tree fixes
+// where every node of it and every deferred sub-tree lands, then the sub-trees are copied in by all threads.
+void splice(const SubTree& src, const std::vector<Task>& tasks, RefBvh& out, unsigned threads) {
     struct Frame { uint32_t local; uint32_t parent_final; int side; };
+    struct Placement { uint32_t task, node_off, rank_off; };
+    std::vector<Placement> placements;
+    size_t total_nodes = src.nodes.size(), total_ranks = src.order.size();
+    for (const BinNode& n : src.nodes)
+        if (n.axis == kDeferred) { total_nodes += tasks[n.a].tree.nodes.size() - 1; total_ranks += tasks[n.a].tree.order.size(); }
+    out.nodes.resize(total_nodes);
+    out.prim_order.resize(total_ranks);
+    uint32_t node_off = 0, rank_off = 0;
     std::vector<Frame> stack;
     stack.push_back({0, 0xFFFFFFFFu, 0});
     while (!stack.empty()) {
-        Frame f = stack.back();
+        const Frame f = stack.back();
         stack.pop_back();
         const BinNode& n = src.nodes[f.local];
-        if (n.axis == kDeferred) {
-            const SubTree& sub = tasks[n.a].tree;
-            const uint32_t node_off = (uint32_t)out.nodes.size(), rank_off = (uint32_t)out.prim_order.size();
-            if (f.parent_final != 0xFFFFFFFFu) {
-                if (f.side == 0) out.nodes[f.parent_final].a = node_off;
-                else { out.nodes[f.parent_final].b = node_off; out.nodes[f.parent_final].right_first = rank_off; }
-            }
-            for (const BinNode& s : sub.nodes) {
-                BinNode c = s;
-                if (c.axis == 3) c.a += rank_off;
-                else { c.a += node_off; c.b += node_off; c.right_first += rank_off; }
-                out.nodes.push_back(c);
-            }
-            out.prim_order.insert(out.prim_order.end(), sub.order.begin(), sub.order.end());
-            if (out.error.empty() && !sub.error.empty()) out.error = sub.error;
-            continue;
-        }
-        const uint32_t me = (uint32_t)out.nodes.size();
+        const uint32_t me = node_off;
         if (f.parent_final != 0xFFFFFFFFu) {
             if (f.side == 0) out.nodes[f.parent_final].a = me;
-            else { out.nodes[f.parent_final].b = me; out.nodes[f.parent_final].right_first = (uint32_t)out.prim_order.size(); }
+            else { out.nodes[f.parent_final].b = me; out.nodes[f.parent_final].right_first = rank_off; }
         }
-        if (n.axis == 3) {
+        if (n.axis == kDeferred) {
+            const SubTree& sub = tasks[n.a].tree;
+            placements.push_back({n.a, node_off, rank_off});
+            node_off += (uint32_t)sub.nodes.size();
+            rank_off += (uint32_t)sub.order.size();
+            if (out.error.empty() && !sub.error.empty()) out.error = sub.error;
+        } else if (n.axis == 3) {
             BinNode c = n;
-            c.a = (uint32_t)out.prim_order.size();
-            out.nodes.push_back(c);
-            for (uint32_t i = 0; i < n.b; ++i) out.prim_order.push_back(src.order[n.a + i]);
+            c.a = rank_off;
+            out.nodes[me] = c;
+            for (uint32_t i = 0; i < n.b; ++i) out.prim_order[rank_off + i] = src.order[n.a + i];
+            node_off += 1;
+            rank_off += n.b;
         } else {
-            out.nodes.push_back(n);
+            out.nodes[me] = n;
+            node_off += 1;
             // pre-order: left subtree is emitted completely before the right one => push right first
             stack.push_back({n.b, me, 1});
             stack.push_back({n.a, me, 0});
         }
     }
+    parallel_chunks(placements.size(), threads, [&](unsigned, size_t b0, size_t e0) {
+        for (size_t k = b0; k < e0; ++k) {
+            const Placement& pl = placements[k];
+            const SubTree& sub = tasks[pl.task].tree;
+            for (size_t j = 0; j < sub.nodes.size(); ++j) {
+                BinNode c = sub.nodes[j];
+                if (c.axis == 3) c.a += pl.rank_off;
+                else { c.a += pl.node_off; c.b += pl.node_off; c.right_first += pl.rank_off; }
+                out.nodes[pl.node_off + j] = c;
+            }
+            std::copy(sub.order.begin(), sub.order.end(), out.prim_order.begin() + pl.rank_off);
+        }
+    });
 }
 
 }  // namespace
@@ -373,7 +386,16 @@ void build_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads, bool all
     }
     timer.mark("primitive bounds");
     Accum all;
-    for (size_t i = 0; i < n; ++i) all.add(items[i].lo, items[i].hi);
+    {   // (a min / max over all items: chunked over the threads, no bit depends on the chunking)
+        std::vector<Accum> part(threads);
+        parallel_chunks(n, threads, [&](unsigned c, size_t b0, size_t e0) {
+            Accum local;
+            for (size_t i = b0; i < e0; ++i) local.add(items[i].lo, items[i].hi);
+            part[c] = local;
+        });
+        for (unsigned c = 0; c < threads; ++c)
+            if (part[c].some) all.add(part[c].lo, part[c].hi);
+    }
     out.bounds = all.box();  // Bvh::bounds bvh.rs:53
     timer.mark("scene bounds");
 
@@ -398,12 +420,8 @@ void build_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads, bool all
         for (auto& th : pool) th.join();
     }
     timer.mark("sub-trees");
-    size_t total_nodes = top.nodes.size();
-    for (const Task& t : tasks) total_nodes += t.tree.nodes.size();
-    out.nodes.reserve(total_nodes);
-    out.prim_order.reserve(n);
     out.error = top.error;
-    splice(top, tasks, out);
+    splice(top, tasks, out, threads);
     timer.mark("splice");
 }
 }  // namespace
