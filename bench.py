@@ -397,7 +397,7 @@ def run_ours(args):
                          "traffic": tk["extend"]["dram_bytes_per_launch"] if "extend" in tk else None, "traffic_detail": tk.get("extend"),
                          "traffic_capture": {k: v for k, v in (traffic or {}).items() if k != "kernels"} or None},
             "other_kernels": [
-                other("k_shade (one path vertex: emission, light sample, BSDF sample, Russian roulette)", totals["closest"], "path vertices", ALGORITHMIC_BYTES_PER_VERTEX,
+                other("shade stage: k_shade_classify + k_shade_class<matte|glass|plastic|metal> + k_shade_miss (one path vertex: emission, light sample, BSDF sample, Russian roulette)", totals["closest"], "path vertices", ALGORITHMIC_BYTES_PER_VERTEX,
                       totals["shade_ms"], "shade"),
                 other("k_wide_persistent<true, ShadowSource> (any-hit traversal of the traced shadow rays)", totals["shadow_traced"], "traced shadow rays",
                       ALGORITHMIC_BYTES_PER_RAY, totals["shadow_ms"], "shadow")],
