@@ -44,7 +44,7 @@ struct Pool {  // structure-of-arrays over `capacity` path slots
     double *beta_r, *beta_g, *beta_b, *L_r, *L_g, *L_b, *prev_bsdf_pdf;
     double *sdx, *sdy, *sdz, *smax, *sc_r, *sc_g, *sc_b;  // pending shadow ray (origin = ox,oy,oz) and its contribution
     uint32_t *id, *pixel, *hash, *shuffled_rev;    // job-relative sample id, film offset, sampler state
-    uint32_t* state;                               // state | bounces << 8 | specular << 16 | shadow_pending << 17 | bad << 18 | contact << 19
+    uint32_t* state;                               // state | bounces << 8 | specular << 16 | shadow_pending << 17 | bad << 18 | contact << 19 | bad L << 20
     // slot indices with a ray to extend / a shadow ray to test this iteration.  Rays for the wide traversal fill a queue from the
     // front; rays that start in a contact shell (state bit 19, fast and F32 modes) go to the reference-order traversal and fill the
     // same array from the back (entry k at capacity - 1 - k): the two never meet, there is at most one entry per slot.
@@ -53,6 +53,7 @@ struct Pool {  // structure-of-arrays over `capacity` path slots
     uint32_t* class_queue;
 };
 constexpr uint32_t kStateContact = 1u << 19;
+constexpr uint32_t kStateBadL = 1u << 20;   // the shadow kernel made L non-finite: the next vertex ends the path (path_integrator.rs:208)
 
 struct Job {
     uint64_t seed;
@@ -130,7 +131,10 @@ __device__ __forceinline__ void settle_shadow(const Pool& p, const Job& job, Cou
         if (!occluded) { r += p.sc_r[i]; g += p.sc_g[i]; b += p.sc_b[i]; }
         flush_path(p, job, counters, i, r, g, b, (st >> 18) & 1u);
     } else if (!occluded) {
-        p.L_r[i] += p.sc_r[i]; p.L_g[i] += p.sc_g[i]; p.L_b[i] += p.sc_b[i];
+        const double r = p.L_r[i] + p.sc_r[i], g = p.L_g[i] + p.sc_g[i], b = p.L_b[i] + p.sc_b[i];
+        p.L_r[i] = r; p.L_g[i] = g; p.L_b[i] = b;
+        // (only the matte class reads L at the next vertex; the others learn of a non-finite L from the state word)
+        if (!(isfinite(r) && isfinite(g) && isfinite(b))) p.state[i] = st | kStateBadL;
     }
 }
 
@@ -735,27 +739,39 @@ __device__ __forceinline__ void shade_vertex(const SceneView& s, const Pool& p, 
     bool bad = (st >> 18) & 1u;
     const V3 ro = mk(p.ox[i], p.oy[i], p.oz[i]), rd = mk(p.dx[i], p.dy[i], p.dz[i]);
     const V3 w_o = neg(rd);
-    Color3 L = mkc(p.L_r[i], p.L_g[i], p.L_b[i]);
+    // Only an emitter adds to the path's radiance at the vertex itself (the light sample is parked for the shadow kernel), and an
+    // emitter is always of the matte class: the other classes neither read nor write L unless the path ends here.
+    constexpr bool kEmits = CLS == CRAY_MAT_MATTE;
+    Color3 L = mkc(0.0, 0.0, 0.0);
+    if (kEmits) L = mkc(p.L_r[i], p.L_g[i], p.L_b[i]);
+    bool L_changed = false;
     Color3 beta = mkc(p.beta_r[i], p.beta_g[i], p.beta_b[i]);
-    const double prev_bsdf_pdf = p.prev_bsdf_pdf[i];
 
     // the path ends here: into the film right away, unless its light sample is still to be tested (then the shadow kernel flushes)
-    auto finish = [&](Color3 Lf, bool shadow_pending) {
-        if (!shadow_pending) { flush_path(p, job, counters, i, Lf.r, Lf.g, Lf.b, bad); return; }
-        p.L_r[i] = Lf.r; p.L_g[i] = Lf.g; p.L_b[i] = Lf.b;
+    auto finish = [&](bool shadow_pending) {
+        if (!shadow_pending) {
+            if (!kEmits) L = mkc(p.L_r[i], p.L_g[i], p.L_b[i]);
+            flush_path(p, job, counters, i, L.r, L.g, L.b, bad);
+            return;
+        }
+        if (L_changed) { p.L_r[i] = L.r; p.L_g[i] = L.g; p.L_b[i] = L.b; }
         p.state[i] = SLOT_DONE | (bounces << 8) | (1u << 17) | ((bad ? 1u : 0u) << 18);
     };
 
     const LeafPrim lp = load_leaf_prim((job.exact ? s.bin_prims : s.wide_prims) + slot);
     V3 location, normal;
     double tu, tv;
-    double hit_t = p.hit_t[i];
+    double hit_t;
     double bu = 0.0, bv = 0.0;
-    if ((lp.kind & 0xFFu) == PRIM_TRIANGLE) {  // the barycentrics the traversal computed for this hit (same code, same bits)
-        double t2 = hit_t;
-        // F32 mode: the f32 traversal chose the triangle, t / u / v are the f64 values of that choice
-        if (!triangle_eval(lp.d, ro, rd, t2, bu, bv) && job.f32) triangle_eval_unchecked(lp.d, ro, rd, t2, bu, bv);
-        if (job.f32) hit_t = t2;
+    if ((lp.kind & 0xFFu) == PRIM_TRIANGLE) {
+        // the distance and barycentrics the traversal computed for this hit (same code, same bits: the stored distance is not even
+        // read).  F32 mode: the f32 traversal chose the triangle, t / u / v are the f64 values of that choice
+        if (!triangle_eval(lp.d, ro, rd, hit_t, bu, bv)) {
+            hit_t = p.hit_t[i];
+            if (job.f32) triangle_eval_unchecked(lp.d, ro, rd, hit_t, bu, bv);
+        }
+    } else {
+        hit_t = p.hit_t[i];
     }
     // Primitive's material / light binding: triangles carry it in the first sector of their shading record
     int32_t material_index, area_light;
@@ -783,9 +799,10 @@ __device__ __forceinline__ void shade_vertex(const SceneView& s, const Pool& p, 
                 L = L + beta * Le;
             } else {
                 const double light_pdf = light_pdf_li(s, light, location, normal, w_o).value * light_pick_pdf(s, (uint32_t)area_light);
-                const double weight = power_heuristic(light_pdf, prev_bsdf_pdf);
+                const double weight = power_heuristic(light_pdf, p.prev_bsdf_pdf[i]);
                 L = L + beta * Le * weight;
             }
+            L_changed = true;
         }
     }
 
@@ -831,11 +848,11 @@ __device__ __forceinline__ void shade_vertex(const SceneView& s, const Pool& p, 
 
     // BSDF sample (:167-195)
     SurfaceSample ss;
-    if (!material_sample<LOBES>(s, material, vs, w_o, normal, tu, tv, ss, bad)) { finish(L, shadow_pending); return; }
-    if (is_black(ss.f)) { finish(L, shadow_pending); return; }
+    if (!material_sample<LOBES>(s, material, vs, w_o, normal, tu, tv, ss, bad)) { finish(shadow_pending); return; }
+    if (is_black(ss.f)) { finish(shadow_pending); return; }
     const double cos_theta = fabs(dot(ss.w_i, normal));
     const double bsdf_pdf = ss.pdf.delta ? 1.0 : ss.pdf.value;
-    if (bsdf_pdf == 0.0) { finish(L, shadow_pending); return; }
+    if (bsdf_pdf == 0.0) { finish(shadow_pending); return; }
     beta = beta * ss.f * cos_theta;
     if (bsdf_pdf != 1.0) beta = beta / bsdf_pdf;   // (x / 1.0 is x, bit for bit: perfectly specular lobes skip three divisions)
 
@@ -844,26 +861,27 @@ __device__ __forceinline__ void shade_vertex(const SceneView& s, const Pool& p, 
         const double max_beta_component = rmax(beta.r, rmax(beta.g, beta.b));
         if (max_beta_component < 1.0) {
             const double q = 1.0 - max_beta_component;
-            if (vs.get(VertexSamples::ROULETTE) < q) { finish(L, shadow_pending); return; }
+            if (vs.get(VertexSamples::ROULETTE) < q) { finish(shadow_pending); return; }
             beta = beta / (1.0 - q);
         }
     }
     // assert!(L.is_finite()); assert!(beta.is_finite()) (:208-209).  L still lacks this vertex's light sample, which
     // the shadow stage adds; k_generate re-checks L when the path is flushed.
-    if (!is_finite3(L) || !is_finite3(beta)) { bad = true; finish(L, shadow_pending); return; }
+    if ((kEmits ? !is_finite3(L) : (st & kStateBadL) != 0u) || !is_finite3(beta)) { bad = true; finish(shadow_pending); return; }
 
     const uint32_t next_bounces = bounces + 1;
     if (next_bounces < s.max_depth && !is_black(beta)) {  // loop condition (:54)
-        p.L_r[i] = L.r; p.L_g[i] = L.g; p.L_b[i] = L.b;
+        if (L_changed) { p.L_r[i] = L.r; p.L_g[i] = L.g; p.L_b[i] = L.b; }
         p.dx[i] = ss.w_i.x; p.dy[i] = ss.w_i.y; p.dz[i] = ss.w_i.z;
         p.beta_r[i] = beta.r; p.beta_g[i] = beta.g; p.beta_b[i] = beta.b;
-        p.prev_bsdf_pdf[i] = bsdf_pdf;
+        if (!ss.is_specular) p.prev_bsdf_pdf[i] = bsdf_pdf;   // (read by the next vertex only after a non-specular bounce)
         p.state[i] = SLOT_ACTIVE | (next_bounces << 8) | ((ss.is_specular ? 1u : 0u) << 16) | ((shadow_pending ? 1u : 0u) << 17) | ((bad ? 1u : 0u) << 18) |
                      (contact ? kStateContact : 0u);
     } else if (shadow_pending) {
-        p.L_r[i] = L.r; p.L_g[i] = L.g; p.L_b[i] = L.b;
+        if (L_changed) { p.L_r[i] = L.r; p.L_g[i] = L.g; p.L_b[i] = L.b; }
         p.state[i] = SLOT_DONE | (next_bounces << 8) | (1u << 17) | ((bad ? 1u : 0u) << 18);
     } else {
+        if (!kEmits) L = mkc(p.L_r[i], p.L_g[i], p.L_b[i]);
         flush_path(p, job, counters, i, L.r, L.g, L.b, bad);
     }
 }
