@@ -62,25 +62,32 @@ def measured_peaks():
 ALGORITHMIC_BYTES_PER_VERTEX = 336  # path state 64 + 64, hit 16, shading attributes 60, material 64, two rays 64, texel 4
 
 
-def library_sha256():
+def source_sha256():
+    """sha256 over the sources libcray_b200.so is built from.  (The binary itself cannot serve: two nvcc builds of the same
+    sources differ in their internal symbol names.)"""
+    import glob
     import hashlib
-    from craytracer_b200 import _abi
-    path = os.environ.get("CRAY_B200_LIB", _abi.LIB_PATH)
+    files = sorted(glob.glob(os.path.join(ROOT, "craytracer_b200", "csrc", "*")) + glob.glob(os.path.join(ROOT, "include", "*.h")))
     h = hashlib.sha256()
-    with open(path, "rb") as f:
-        for chunk in iter(lambda: f.read(1 << 20), b""):
-            h.update(chunk)
+    for path in files:
+        if os.path.isfile(path):
+            h.update(os.path.relpath(path, ROOT).encode() + b"\0")
+            with open(path, "rb") as f:
+                h.update(f.read())
     return h.hexdigest()
 
 
 def profiled_traffic():
     """DRAM bytes per launch of each kernel from the committed `ncu --set full` capture of this workload (tools/final_capture.sh
-    -> tools/kernel_traffic.py -> profiles/kernel_traffic.json).  The capture names the library it was taken on by sha256: if
-    that is not the library being timed now, the figures are not this binary's and nothing is reported (null)."""
+    -> tools/kernel_traffic.py -> profiles/kernel_traffic.json).  The capture names the sources of the library it was taken on by
+    sha256: if the library being timed now is built from other sources, the figures are not this code's and nothing is reported
+    (null).  CRAY_B200_LIB (a tuning variant) never matches."""
     try:
+        if os.environ.get("CRAY_B200_LIB"):
+            return None
         with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
             data = json.load(f)
-        if data.get("library_sha256") != library_sha256():
+        if data.get("source_sha256") != source_sha256():
             return None
         return data
     except Exception:

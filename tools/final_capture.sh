@@ -3,7 +3,8 @@
 # usage: TAG=r1c bash tools/final_capture.sh     (outputs under gpurun_out/)
 TAG=${TAG:-final}
 O=gpurun_out
-sha256sum craytracer_b200/libcray_b200.so > $O/lib_sha_$TAG.txt   # ties the ncu figures to this binary (tools/kernel_traffic.py)
+python -c "import bench; print(bench.source_sha256())" > $O/lib_sha_$TAG.txt   # ties the ncu figures to these sources (tools/kernel_traffic.py)
+sha256sum craytracer_b200/libcray_b200.so >> $O/lib_sha_$TAG.txt
 python bench.py > $O/bench_$TAG.json 2> $O/bench_$TAG.err
 python bench.py --impl reference > $O/bench_${TAG}_reference.json 2> $O/bench_${TAG}_reference.err
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_$TAG.log 2>&1

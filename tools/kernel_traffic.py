@@ -3,8 +3,9 @@
 
 usage: kernel_traffic.py report.ncu-rep lib_sha.txt "what was captured" [out.json]
 
-`lib_sha.txt` is the `sha256sum craytracer_b200/libcray_b200.so` written ON THE GPU BOX by tools/final_capture.sh beside the
-report: bench.py reports these figures as `roofline.traffic` only while the library it times has the same hash.  Per kernel
+`lib_sha.txt` is written ON THE GPU BOX by tools/final_capture.sh beside the report: the sha256 of the library's sources
+(bench.source_sha256; first line) and of the binary (second line, informational: nvcc builds are not bit-reproducible).  bench.py
+reports these figures as `roofline.traffic` only while the library it times is built from the same sources.  Per kernel
 class the launch with the longest duration is taken (the capture window sits where all path slots are live)."""
 import csv
 import io
@@ -53,8 +54,8 @@ def main():
     parts = [kernels[k] for k in kernels if k.startswith("shade_")]
     if parts:
         kernels["shade"] = {f: sum(x[f] for x in parts) for f in ("dram_bytes_per_launch", "dram_read", "dram_write", "launch_ms_under_ncu")}
-    sha = open(sha_file).read().split()[0]
-    data = {"library_sha256": sha, "source": what, "report": rep, "kernels": kernels}
+    lines = [ln.split()[0] for ln in open(sha_file).read().splitlines() if ln.strip()]
+    data = {"source_sha256": lines[0], "library_sha256": lines[1] if len(lines) > 1 else None, "source": what, "report": rep, "kernels": kernels}
     with open(out_path, "w") as f:
         json.dump(data, f, indent=1)
         f.write("\n")
