@@ -503,12 +503,17 @@ __device__ __forceinline__ void camera_ray(const DevCamera& c, double fu, double
     d = xf_vector(c.world_from_camera, rd);
 }
 
-// Block-wide exclusive rank of the threads with `pred` (ascending thread order) and their total.  `s_warp` = 8 words of shared
-// memory; ends with a barrier, so it can be called again right away.
-__device__ __forceinline__ uint32_t block_rank_256(bool pred, uint32_t* s_warp, uint32_t& total) {
+// Block-wide exclusive prefix sum of `value` over the 256 threads (ascending thread order) and its total.  `s_warp` = 8 words of
+// shared memory; ends with a barrier, so it can be called again right away.
+__device__ __forceinline__ uint32_t block_scan_256(uint32_t value, uint32_t* s_warp, uint32_t& total) {
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
-    if (lane == 0) s_warp[warp] = __popc(m);
+    uint32_t incl = value;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= (unsigned)d) incl += up;
+    }
+    if (lane == 31u) s_warp[warp] = incl;
     __syncthreads();
     uint32_t before = 0, all = 0;
 #pragma unroll
@@ -519,106 +524,100 @@ __device__ __forceinline__ uint32_t block_rank_256(bool pred, uint32_t* s_warp, 
     }
     __syncthreads();
     total = all;
-    return before + __popc(m & ((1u << lane) - 1u));
+    return before + incl - value;
 }
 
-// The same for two disjoint predicates in one pass (counts packed 16 + 16 bits).
-__device__ __forceinline__ void block_rank2_256(bool pa, bool pb, uint32_t* s_warp, uint32_t& rank_a, uint32_t& rank_b, uint32_t& total_a, uint32_t& total_b) {
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const unsigned ma = __ballot_sync(0xFFFFFFFFu, pa), mb = __ballot_sync(0xFFFFFFFFu, pb);
-    if (lane == 0) s_warp[warp] = __popc(ma) | (__popc(mb) << 16);
-    __syncthreads();
-    uint32_t before = 0, all = 0;
-#pragma unroll
-    for (unsigned w = 0; w < 8; ++w) {
-        const uint32_t c = s_warp[w];
-        before += w < warp ? c : 0u;
-        all += c;
-    }
-    __syncthreads();
-    total_a = all & 0xFFFFu; total_b = all >> 16;
-    rank_a = (before & 0xFFFFu) + __popc(ma & ((1u << lane) - 1u));
-    rank_b = (before >> 16) + __popc(mb & ((1u << lane) - 1u));
-}
-
-// One block = 256 consecutive path slots.  Finished paths are flushed by their own thread; the slots to refill are then
-// compacted, so that the camera-ray code (SipHash, four Sobol values, f64 camera transform) runs on full warps instead of on the
-// scattered third of the lanes whose path happened to end -- and the sample ids and the extend-queue range of the whole block
-// are each claimed with ONE atomic.
+// One block = 1024 consecutive path slots, four per thread (the scan of the slot states is what this kernel does most: a block
+// per 256 slots spent its time in barriers).  The slots to refill are compacted, so that the camera-ray code (SipHash, four Sobol
+// values, f64 camera transform) runs on full warps instead of on the scattered lanes whose path happened to end -- and the sample
+// ids and the extend-queue range of the whole block are each claimed with ONE atomic.  (Finished paths were flushed where they
+// ended, flush_path; a slot still found DONE here is flushed as a fallback.)
+constexpr uint32_t kGenSlots = 4, kGenBlock = 256u * kGenSlots;
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneView s, const __grid_constant__ Pool p, const __grid_constant__ Job job, Counters* counters) {
     __shared__ uint32_t s_warp[8];
-    __shared__ uint32_t s_list[256];
+    __shared__ uint32_t s_list[kGenBlock];
     __shared__ unsigned long long s_base[3];
-    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    const bool in_range = i < p.capacity;
-    uint32_t st = in_range ? p.state[i] : 0xFFu;  // 0xFF: no slot
-    if (st_state(st) == SLOT_DONE) {
-        // flush: craytracer.rs:177-188 accumulates the sample into its pixel; a sample on which the reference would
-        // have panicked (path_integrator.rs:208-209 and the asserts of its callees) is dropped and counted
-        const double r = p.L_r[i], g = p.L_g[i], b = p.L_b[i];
-        const bool bad = ((st >> 18) & 1u) || !(isfinite(r) && isfinite(g) && isfinite(b));
-        if (bad) {
-            atomicAdd(&counters->nan_samples, 1ull);
-        } else if (job.film) {
-            double* px = job.film + 3ull * p.pixel[i];
-            atomicAdd(px, r); atomicAdd(px + 1, g); atomicAdd(px + 2, b);
+    const uint32_t first = (blockIdx.x * 256u + threadIdx.x) * kGenSlots;
+    uint32_t st[kGenSlots];
+    uint32_t n_mine = 0;   // empty slots among this thread's
+#pragma unroll
+    for (uint32_t k = 0; k < kGenSlots; ++k) {
+        const uint32_t i = first + k;
+        st[k] = i < p.capacity ? p.state[i] : 0xFFu;  // 0xFF: no slot
+        if (st_state(st[k]) == SLOT_DONE) {
+            flush_path(p, job, counters, i, p.L_r[i], p.L_g[i], p.L_b[i], (st[k] >> 18) & 1u);
+            st[k] = SLOT_EMPTY;
         }
-        if (job.out_rgb) {
-            double* dst = job.out_rgb + 3ull * p.id[i];
-            dst[0] = r; dst[1] = g; dst[2] = b;
-        }
-        st = SLOT_EMPTY;
-        p.state[i] = st;
+        n_mine += st_state(st[k]) == SLOT_EMPTY ? 1u : 0u;
     }
-    // the empty slots of this block, compacted
-    const bool empty = st_state(st) == SLOT_EMPTY;
+    // the empty slots of this block, compacted in ascending order
     uint32_t n_empty;
-    const uint32_t rank = block_rank_256(empty, s_warp, n_empty);
-    if (empty) s_list[rank] = i;
+    const uint32_t my_rank = block_scan_256(n_mine, s_warp, n_empty);
+    {
+        uint32_t r = my_rank;
+#pragma unroll
+        for (uint32_t k = 0; k < kGenSlots; ++k)
+            if (st_state(st[k]) == SLOT_EMPTY) s_list[r++] = first + k;
+    }
     if (threadIdx.x == 0 && n_empty) s_base[0] = atomicAdd(&counters->next_id, (unsigned long long)n_empty);
     __syncthreads();
     const unsigned long long id_base = n_empty ? s_base[0] : 0ull;
-    if (threadIdx.x < n_empty) {
-        const unsigned long long id = id_base + threadIdx.x;
-        if (id < job.n_total) {
-            const uint32_t slot = s_list[threadIdx.x];
-            uint32_t x, y, si;
-            if (job.lx) { x = job.lx[id]; y = job.ly[id]; si = job.ls[id]; }
-            else {
-                const uint32_t po = job.pixel_order[id % job.n_pixels];
-                x = po & 0xFFFFu; y = po >> 16;
-                si = job.sample_begin + (uint32_t)(id / job.n_pixels);
-            }
-            PixelSampler smp;
-            smp.start_pixel(job.seed, x, y, si);
-            const double fu = smp.sample_1d(job.sobol), fv = smp.sample_1d(job.sobol);
-            const double lu = smp.sample_1d(job.sobol), lv = smp.sample_1d(job.sobol);
-            V3 o, d;
-            camera_ray(s.camera, fu, fv, lu, lv, x, y, o, d);
-            p.ox[slot] = o.x; p.oy[slot] = o.y; p.oz[slot] = o.z;
-            p.dx[slot] = d.x; p.dy[slot] = d.y; p.dz[slot] = d.z;
-            p.beta_r[slot] = 1.0; p.beta_g[slot] = 1.0; p.beta_b[slot] = 1.0;
-            p.L_r[slot] = 0.0; p.L_g[slot] = 0.0; p.L_b[slot] = 0.0;
-            p.prev_bsdf_pdf[slot] = 0.0;
-            p.hit_slot[slot] = CRAY_NO_HIT;  // a camera ray leaves no surface (F32 mode's self-intersection rule)
-            p.id[slot] = (uint32_t)id;
-            p.pixel[slot] = x + y * s.camera.width;
-            p.hash[slot] = smp.hash;
-            p.shuffled_rev[slot] = smp.shuffled_rev;
-            p.state[slot] = SLOT_ACTIVE | (1u << 16);  // bounces = 0, is_specular_bounce = true (path_integrator.rs:50)
+    for (uint32_t j = threadIdx.x; j < n_empty; j += 256u) {
+        const unsigned long long id = id_base + j;
+        if (id >= job.n_total) break;
+        const uint32_t slot = s_list[j];
+        uint32_t x, y, si;
+        if (job.lx) { x = job.lx[id]; y = job.ly[id]; si = job.ls[id]; }
+        else {
+            const uint32_t po = job.pixel_order[id % job.n_pixels];
+            x = po & 0xFFFFu; y = po >> 16;
+            si = job.sample_begin + (uint32_t)(id / job.n_pixels);
         }
+        PixelSampler smp;
+        smp.start_pixel(job.seed, x, y, si);
+        const double fu = smp.sample_1d(job.sobol), fv = smp.sample_1d(job.sobol);
+        const double lu = smp.sample_1d(job.sobol), lv = smp.sample_1d(job.sobol);
+        V3 o, d;
+        camera_ray(s.camera, fu, fv, lu, lv, x, y, o, d);
+        p.ox[slot] = o.x; p.oy[slot] = o.y; p.oz[slot] = o.z;
+        p.dx[slot] = d.x; p.dy[slot] = d.y; p.dz[slot] = d.z;
+        p.beta_r[slot] = 1.0; p.beta_g[slot] = 1.0; p.beta_b[slot] = 1.0;
+        p.L_r[slot] = 0.0; p.L_g[slot] = 0.0; p.L_b[slot] = 0.0;
+        p.prev_bsdf_pdf[slot] = 0.0;
+        p.hit_slot[slot] = CRAY_NO_HIT;  // a camera ray leaves no surface (F32 mode's self-intersection rule)
+        p.id[slot] = (uint32_t)id;
+        p.pixel[slot] = x + y * s.camera.width;
+        p.hash[slot] = smp.hash;
+        p.shuffled_rev[slot] = smp.shuffled_rev;
+        p.state[slot] = SLOT_ACTIVE | (1u << 16);  // bounces = 0, is_specular_bounce = true (path_integrator.rs:50)
     }
     // every live slot has a ray to extend this iteration: the block's slots go to the queue in ascending order -- to its back
-    // part if the ray starts in a contact shell (k_shade found out) and needs the reference-order traversal
-    const bool live = st_state(st) == SLOT_ACTIVE || (empty && id_base + rank < job.n_total);
-    const bool contact = live && (st & kStateContact) && st_state(st) == SLOT_ACTIVE;
-    uint32_t n_wide, n_contact, qrank, crank;
-    block_rank2_256(live && !contact, contact, s_warp, qrank, crank, n_wide, n_contact);
+    // part if the ray starts in a contact shell (the shade stage found out) and needs the reference-order traversal
+    uint32_t live_mask = 0, contact_mask = 0;
+    {
+        uint32_t r = my_rank;
+#pragma unroll
+        for (uint32_t k = 0; k < kGenSlots; ++k) {
+            const bool empty = st_state(st[k]) == SLOT_EMPTY, active = st_state(st[k]) == SLOT_ACTIVE;
+            const bool live = active || (empty && id_base + r < job.n_total);
+            r += empty ? 1u : 0u;
+            const bool contact = active && (st[k] & kStateContact);
+            live_mask |= (live && !contact ? 1u : 0u) << k;
+            contact_mask |= (contact ? 1u : 0u) << k;
+        }
+    }
+    uint32_t totals;
+    const uint32_t ranks = block_scan_256(__popc(live_mask) | (__popc(contact_mask) << 16), s_warp, totals);
+    const uint32_t n_wide = totals & 0xFFFFu, n_contact = totals >> 16;
     if (threadIdx.x == 0 && n_wide) s_base[1] = atomicAdd(&counters->n_extend, (unsigned long long)n_wide);
     if (threadIdx.x == 32 && n_contact) s_base[2] = atomicAdd(&counters->n_extend_contact, (unsigned long long)n_contact);
     __syncthreads();
-    if (contact) p.extend_queue[p.capacity - 1u - (uint32_t)(s_base[2] + crank)] = i;
-    else if (live) p.extend_queue[s_base[1] + qrank] = i;
+    uint32_t qrank = ranks & 0xFFFFu, crank = ranks >> 16;
+#pragma unroll
+    for (uint32_t k = 0; k < kGenSlots; ++k) {
+        if (contact_mask & (1u << k)) p.extend_queue[p.capacity - 1u - (uint32_t)(s_base[2] + crank++)] = first + k;
+        else if (live_mask & (1u << k)) p.extend_queue[s_base[1] + qrank++] = first + k;
+    }
 }
 
 // Start of a wavefront iteration: rolls the queue lengths of the previous one into the run's totals and clears the per-iteration
@@ -1070,7 +1069,7 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
     CRAY_CUDA(cudaEventCreate(&ev.e0)); CRAY_CUDA(cudaEventCreate(&ev.e1));
     CRAY_CUDA(cudaEventCreateWithFlags(&ev.gen_done, cudaEventDisableTiming));
     CRAY_CUDA(cudaEventRecord(ev.e0, stream));
-    const unsigned g256 = (capacity + 255) / 256;
+    const unsigned g256 = (capacity + kGenBlock - 1) / kGenBlock;   // k_generate: 1024 slots per block
     const unsigned gx = (unsigned)std::min<uint64_t>(kExactBlocks, (capacity + 127) / 128);
     const unsigned gp = ps->persistent_blocks, gs = ps->shadow_blocks;
     // fast mode: rays that start in a contact shell go to the reference-order kernels (only scenes with marked primitives have any)
