@@ -142,6 +142,7 @@ EXTRA_SIGNATURES = {
     "cray_debug_check_wide_bvh": (C.c_int, [C.POINTER(SceneDesc), _P]),
     "cray_debug_wide_stats": (C.c_int, [_P]),
     "cray_debug_find_contacts": (C.c_int, [C.POINTER(SceneDesc), _P, _P]),
+    "cray_debug_build_reference_bvh_on": (C.c_int, [C.POINTER(SceneDesc), C.c_int, C.POINTER(C.POINTER(BvhNodeDump)), C.POINTER(C.c_uint64), C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint64)]),
     "cray_debug_tokenize": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     "cray_debug_parse_raw_value": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
 }

@@ -22,12 +22,7 @@ constexpr double kTraversalCost = 1.0 / 8.0; // bvh.rs:236
 constexpr size_t kMaxLeaf = 4;               // bvh.rs:237
 constexpr uint32_t kDeferred = 0xFFFFFFFFu;
 
-struct Item {  // PrimitiveInfo (bvh.rs:149-154); the centroid is recomputed from the box (same expression, same bits)
-    double lo[3], hi[3];
-    uint32_t prim;
-    uint32_t bucket;
-};
-static_assert(sizeof(Item) == 56, "Item layout");
+using Item = BuildItem;
 
 inline Box3 item_box(const Item& it) { return {mk(it.lo[0], it.lo[1], it.lo[2]), mk(it.hi[0], it.hi[1], it.hi[2])}; }
 inline double centroid_axis(const Item& it, int axis) { return (it.lo[axis] + it.hi[axis]) * 0.5; }
@@ -355,15 +350,18 @@ Box3 primitive_bounds(const cray_scene_desc& d, uint64_t prim) {  // Shape::boun
 }
 
 namespace {
-void build_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads, bool all_axes);
+void build_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads, bool all_axes, int gpu_device);
+thread_local bool t_last_build_on_device = false;
 }
-void build_reference_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads) { build_bvh(d, out, threads, false); }
-void build_quality_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads) { build_bvh(d, out, threads, true); }
+bool last_reference_build_was_on_device() { return t_last_build_on_device; }
+void build_reference_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads, int gpu_device) { build_bvh(d, out, threads, false, gpu_device); }
+void build_quality_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads) { build_bvh(d, out, threads, true, -1); }
 namespace {
-void build_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads, bool all_axes) {
+void build_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads, bool all_axes, int gpu_device) {
     PhaseTimer timer;
     const size_t n = (size_t)d.n_primitives;
     out = RefBvh{};
+    if (!all_axes) t_last_build_on_device = false;
     if (n == 0) { out.error = "no primitives"; return; }
     if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
     std::vector<Item> items(n);
@@ -398,6 +396,19 @@ void build_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads, bool all
     }
     out.bounds = all.box();  // Bvh::bounds bvh.rs:53
     timer.mark("scene bounds");
+    if (!all_axes && gpu_device >= 0 && n > (1u << 16)) {
+        const char* e = std::getenv("CRAY_GPU_BUILD");
+        if (!e || std::atoi(e) != 0) {
+            std::string why;
+            if (build_reference_bvh_gpu(items.data(), n, gpu_device, out, why)) {
+                timer.mark("tree on the device");
+                t_last_build_on_device = true;
+                return;
+            }
+            if (timer.on) std::fprintf(stderr, "[cray build] device build not used: %s\n", why.c_str());
+            out.nodes.clear(); out.prim_order.clear(); out.error.clear();
+        }
+    }
 
     std::vector<Task> tasks;
     SubTree top;

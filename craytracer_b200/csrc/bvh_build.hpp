@@ -48,7 +48,19 @@ struct RefBvh {
 
 // Bounds of primitive i exactly as Shape::bounds computes them (src/shape.rs:402-438).
 Box3 primitive_bounds(const cray_scene_desc& d, uint64_t prim);
-void build_reference_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads = 0);
+// `gpu_device` >= 0: scenes of more than 2^16 primitives build the tree on that device (bvh_build_gpu.cu: the same tree, node for
+// node); the host builder takes over if there is no usable device or CRAY_GPU_BUILD=0.
+void build_reference_bvh(const cray_scene_desc& d, RefBvh& out, unsigned threads = 0, int gpu_device = -1);
+
+struct BuildItem {  // PrimitiveInfo (bvh.rs:149-154); the centroid is recomputed from the box (same expression, same bits)
+    double lo[3], hi[3];
+    uint32_t prim;
+    uint32_t bucket;
+};
+static_assert(sizeof(BuildItem) == 56, "BuildItem layout");
+// The tree over `items` (their boxes, in primitive order) built on `device`; false (with the reason) if that did not happen.
+bool build_reference_bvh_gpu(const BuildItem* items, size_t n, int device, RefBvh& out, std::string& why);
+bool last_reference_build_was_on_device();   // of this thread's last build_reference_bvh call (tests)
 // The same builder choosing, at every node, the cheapest of the three axes' best binned splits instead of the reference's
 // longest-centroid-axis rule: the tree the 8-wide BVH can be collapsed from (hits do not depend on it: the f64 leaf tests decide,
 // and exact-t ties are resolved on the reference tree).

@@ -211,12 +211,12 @@ struct HostBuild {
 };
 
 // Scene::new (scene.rs:25-53) on the host: the reference BVH, its wide collapse, and every flat array of device_types.cuh.
-int build_host_side(const cray_scene_desc* d, uint32_t build_flags, HostBuild& hb) {
+int build_host_side(const cray_scene_desc* d, uint32_t build_flags, HostBuild& hb, int device) {
     hb.build_flags = build_flags;
     RefBvh& ref = hb.ref;
     WideBvh& wide = hb.wide;
     auto t0 = std::chrono::steady_clock::now();
-    build_reference_bvh(*d, ref);
+    build_reference_bvh(*d, ref, 0, device);
     if (!ref.error.empty()) { set_error(ref.error); return CRAY_E_BVH; }
     if (build_flags & CRAY_BUILD_FAST) {
         // CRAY_WIDE_TREE=sah3 (tuning): collapse the wide BVH from a second tree built with three-axis SAH splits
@@ -478,11 +478,17 @@ const char* cray_last_error(void) { return cray::last_error().c_str(); }
 const char* cray_version(void) { return "craytracer_b200 0.1 (sm_100a)"; }
 void cray_free(void* p) { std::free(p); }
 
+// Tests: the same dump with the tree built on `device` (bvh_build_gpu.cu); CRAY_E_UNSUPPORTED if the device build was not used.
+int cray_debug_build_reference_bvh_on(const cray_scene_desc* desc, int device, cray_bvh_node_dump** nodes, uint64_t* n_nodes, uint32_t** prim_order, uint64_t* n_prims);
 int cray_build_reference_bvh(const cray_scene_desc* desc, cray_bvh_node_dump** nodes, uint64_t* n_nodes, uint32_t** prim_order, uint64_t* n_prims) {
+    return cray_debug_build_reference_bvh_on(desc, -1, nodes, n_nodes, prim_order, n_prims);
+}
+int cray_debug_build_reference_bvh_on(const cray_scene_desc* desc, int device, cray_bvh_node_dump** nodes, uint64_t* n_nodes, uint32_t** prim_order, uint64_t* n_prims) {
     if (!desc || desc->n_primitives == 0 || !nodes || !n_nodes || !prim_order || !n_prims) { set_error("bad arguments"); return CRAY_E_INVALID; }
     RefBvh bvh;
-    build_reference_bvh(*desc, bvh);
+    build_reference_bvh(*desc, bvh, 0, device);
     if (!bvh.error.empty()) { set_error(bvh.error); return CRAY_E_BVH; }
+    if (device >= 0 && !last_reference_build_was_on_device()) { set_error("the tree was built on the host"); return CRAY_E_UNSUPPORTED; }
     auto* out = (cray_bvh_node_dump*)std::malloc(sizeof(cray_bvh_node_dump) * bvh.nodes.size());
     auto* order = (uint32_t*)std::malloc(sizeof(uint32_t) * bvh.prim_order.size());
     for (size_t i = 0; i < bvh.nodes.size(); ++i) {
@@ -521,7 +527,7 @@ int cray_scene_create_multi(const cray_scene_desc* d, const int* devices, int n,
     rc = check_devices(devices, n);
     if (rc != CRAY_OK) return rc;
     HostBuild hb;
-    rc = build_host_side(d, build_flags, hb);
+    rc = build_host_side(d, build_flags, hb, devices[0]);
     if (rc != CRAY_OK) return rc;
     // one uploading thread per device (cray_last_error is thread-local: carry a failure back to this thread)
     std::vector<int> rcs(n, CRAY_OK);

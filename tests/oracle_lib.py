@@ -172,13 +172,13 @@ class OracleScene:
         return m[:16].reshape(4, 4), m[16:].reshape(4, 4)
 
 
-def product_bvh(host_scene):
-    """cray_build_reference_bvh: the product's host BVH builder, dumped in the oracle's format."""
+def product_bvh(host_scene, device=-1):
+    """cray_build_reference_bvh: the product's BVH builder (host; `device` >= 0: the GPU builder), dumped in the oracle's format."""
     L = _abi.lib()
     nodes_p = C.POINTER(_abi.BvhNodeDump)()
     order_p = C.POINTER(C.c_uint32)()
     n_nodes, n_prims = C.c_uint64(), C.c_uint64()
-    rc = L.cray_build_reference_bvh(host_scene.desc_ptr, C.byref(nodes_p), C.byref(n_nodes), C.byref(order_p), C.byref(n_prims))
+    rc = L.cray_debug_build_reference_bvh_on(host_scene.desc_ptr, device, C.byref(nodes_p), C.byref(n_nodes), C.byref(order_p), C.byref(n_prims))
     if rc != 0:
         raise RuntimeError(L.cray_last_error().decode())
     nodes = np.frombuffer(C.string_at(nodes_p, n_nodes.value * 64), dtype=_abi.BVH_NODE_DTYPE).copy()
