@@ -62,18 +62,20 @@ def measured_peaks():
 ALGORITHMIC_BYTES_PER_VERTEX = 336  # path state 64 + 64, hit 16, shading attributes 60, material 64, two rays 64, texel 4
 
 
+KERNEL_SOURCES = ["wavefront.cu", "traverse.cuh", "shapes.cuh", "shading.cuh", "sampler.cuh", "cray_math.cuh", "device_types.cuh", "bvh_build.hpp", "Makefile"]
+
+
 def source_sha256():
-    """sha256 over the sources libcray_b200.so is built from.  (The binary itself cannot serve: two nvcc builds of the same
-    sources differ in their internal symbol names.)"""
-    import glob
+    """sha256 over the sources the wavefront kernels of libcray_b200.so are compiled from (kernels, their headers, the node and
+    record layouts, the compiler flags).  (The binary itself cannot serve: two nvcc builds of the same sources differ in their
+    internal symbol names.)"""
     import hashlib
-    files = sorted(glob.glob(os.path.join(ROOT, "craytracer_b200", "csrc", "*")) + glob.glob(os.path.join(ROOT, "include", "*.h")))
     h = hashlib.sha256()
-    for path in files:
-        if os.path.isfile(path):
-            h.update(os.path.relpath(path, ROOT).encode() + b"\0")
-            with open(path, "rb") as f:
-                h.update(f.read())
+    for name in KERNEL_SOURCES + ["../../include/cray_b200.h"]:
+        path = os.path.normpath(os.path.join(ROOT, "craytracer_b200", "csrc", name))
+        h.update(os.path.relpath(path, ROOT).encode() + b"\0")
+        with open(path, "rb") as f:
+            h.update(f.read())
     return h.hexdigest()
 
 

@@ -526,6 +526,9 @@ int cray_scene_create_multi(const cray_scene_desc* d, const int* devices, int n,
     build_flags |= CRAY_BUILD_EXACT;  // the binary tree also resolves exact-t ties for the fast mode
     rc = check_devices(devices, n);
     if (rc != CRAY_OK) return rc;
+    // (the first device's context exists before the build is timed: the tree of a large scene is built there)
+    if (cudaSetDevice(devices[0]) == cudaSuccess) cudaFree(nullptr);
+    cudaGetLastError();
     HostBuild hb;
     rc = build_host_side(d, build_flags, hb, devices[0]);
     if (rc != CRAY_OK) return rc;
