@@ -60,6 +60,7 @@ struct BuildItem {  // PrimitiveInfo (bvh.rs:149-154); the centroid is recompute
 static_assert(sizeof(BuildItem) == 56, "BuildItem layout");
 // The tree over `items` (their boxes, in primitive order) built on `device`; false (with the reason) if that did not happen.
 bool build_reference_bvh_gpu(const BuildItem* items, size_t n, int device, RefBvh& out, std::string& why);
+void finish_device_build_release();           // waits for the background release of the last device build's buffers
 bool last_reference_build_was_on_device();   // of this thread's last build_reference_bvh call (tests)
 // The same builder choosing, at every node, the cheapest of the three axes' best binned splits instead of the reference's
 // longest-centroid-axis rule: the tree the 8-wide BVH can be collapsed from (hits do not depend on it: the f64 leaf tests decide,

@@ -20,7 +20,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bvh_build.hpp"
@@ -453,7 +455,15 @@ struct DeviceBuffers {   // freed on every return path
     ~DeviceBuffers() { for (void* q : ptrs) cudaFree(q); }
 };
 
+std::mutex g_release_mutex;
+std::thread g_release_thread;
+
 }  // namespace
+
+void finish_device_build_release() {
+    std::lock_guard<std::mutex> lock(g_release_mutex);
+    if (g_release_thread.joinable()) g_release_thread.join();
+}
 
 bool build_reference_bvh_gpu(const BuildItem* host_items, size_t n_items, int device, RefBvh& out, std::string& why) {
     if (n_items < 2 * kSmall || n_items > 0x7FFFFFFFull) { why = "too few primitives for the device build"; return false; }
@@ -467,6 +477,12 @@ bool build_reference_bvh_gpu(const BuildItem* host_items, size_t n_items, int de
     cudaFree(nullptr);   // (creates the device context if this is the process's first CUDA work)
     timer.mark("gpu build: device context");
     const uint32_t n = (uint32_t)n_items;
+    // the host arrays the tree is downloaded into are sized (and their pages touched) while the device works
+    struct Toucher {
+        std::thread th;
+        ~Toucher() { if (th.joinable()) th.join(); }
+    } toucher;
+    toucher.th = std::thread([&out, n] { out.nodes.resize(2ull * n); out.prim_order.resize(n); });
     const uint32_t node_capacity = (uint32_t)std::min<uint64_t>(2ull * n, (uint64_t)n / 16 + 4096);   // top of the tree only
     DeviceBuffers buf;
     BuildItem* d_items; uint32_t *d_seg, *d_slot, *d_active, *d_next, *d_small, *d_fl, *d_fr, *d_sl, *d_sr, *d_pl, *d_pr, *d_counters, *d_pre, *d_order;
@@ -559,15 +575,25 @@ bool build_reference_bvh_gpu(const BuildItem* host_items, size_t n_items, int de
     cudaMemcpy(d_pre, pre.data(), sizeof(uint32_t) * n_top, cudaMemcpyHostToDevice);
     k_emit<<<(n_top + 127) / 128, 128>>>(d_nodes, d_pre, n_top, d_local, d_out);
     k_prim_order<<<item_blocks, 256>>>(d_items, d_order, n);
-    out.nodes.resize(total_nodes);
-    out.prim_order.resize(n);
+    toucher.th.join();
+    out.nodes.resize(total_nodes);   // (shrinks: a tree over n items has at most 2n - 1 nodes)
     cudaMemcpy(out.nodes.data(), d_out, sizeof(BinNode) * total_nodes, cudaMemcpyDeviceToHost);
     cudaMemcpy(out.prim_order.data(), d_order, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost);
     if (!check("assembly")) return false;
     timer.mark("gpu build: assembly + download");
-    for (void* q : buf.ptrs) cudaFree(q);
-    buf.ptrs.clear();
-    timer.mark("gpu build: release");
+    // the ~6 GB of build buffers are released behind the caller's back (cudaFree of the first build of a process was measured at
+    // 0.85 s): finish_device_build_release() waits for it
+    finish_device_build_release();
+    {
+        std::vector<void*> ptrs;
+        ptrs.swap(buf.ptrs);
+        std::lock_guard<std::mutex> lock(g_release_mutex);
+        g_release_thread = std::thread([ptrs, device] {
+            if (cudaSetDevice(device) == cudaSuccess)
+                for (void* q : ptrs) cudaFree(q);
+            cudaGetLastError();
+        });
+    }
     return true;
 }
 

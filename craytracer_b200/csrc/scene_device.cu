@@ -488,6 +488,7 @@ int cray_debug_build_reference_bvh_on(const cray_scene_desc* desc, int device, c
     RefBvh bvh;
     build_reference_bvh(*desc, bvh, 0, device);
     if (!bvh.error.empty()) { set_error(bvh.error); return CRAY_E_BVH; }
+    finish_device_build_release();
     if (device >= 0 && !last_reference_build_was_on_device()) { set_error("the tree was built on the host"); return CRAY_E_UNSUPPORTED; }
     auto* out = (cray_bvh_node_dump*)std::malloc(sizeof(cray_bvh_node_dump) * bvh.nodes.size());
     auto* order = (uint32_t*)std::malloc(sizeof(uint32_t) * bvh.prim_order.size());
@@ -531,6 +532,7 @@ int cray_scene_create_multi(const cray_scene_desc* d, const int* devices, int n,
     cudaGetLastError();
     HostBuild hb;
     rc = build_host_side(d, build_flags, hb, devices[0]);
+    finish_device_build_release();   // (the build buffers of a device-built tree were freed while the host collapsed it)
     if (rc != CRAY_OK) return rc;
     // one uploading thread per device (cray_last_error is thread-local: carry a failure back to this thread)
     std::vector<int> rcs(n, CRAY_OK);
