@@ -216,6 +216,35 @@ int build_host_side(const cray_scene_desc* d, uint32_t build_flags, HostBuild& h
     RefBvh& ref = hb.ref;
     WideBvh& wide = hb.wide;
     auto t0 = std::chrono::steady_clock::now();
+    // the per-primitive shading records do not depend on the trees: they are built beside them (the host cores are idle while the
+    // device builds the reference tree)
+    std::thread shading_records([&hb, d] {
+        const size_t np = (size_t)d->n_primitives;
+        // per-primitive shading records for triangles (flat ones are flagged in their LeafPrim, see make_leaf_prim)
+        std::vector<TriShade>& tri_shade = hb.tri_shade;
+        tri_shade.resize(d->n_triangles ? np : 0);
+        {
+            const unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+            std::vector<std::thread> pool;
+            auto work = [&](unsigned t0) {
+                for (size_t i = t0; i < tri_shade.size(); i += nt) {
+                    const cray_primitive_desc& p = d->primitives[i];
+                    TriShade& ts = tri_shade[i];
+                    std::memset(&ts, 0, sizeof(ts));
+                    if (p.shape_kind != CRAY_SHAPE_TRIANGLE) continue;
+                    const cray_triangle_desc& t = d->triangles[p.shape_index];
+                    std::memcpy(ts.n0, t.n0, 24); std::memcpy(ts.n01, t.n01, 24); std::memcpy(ts.n02, t.n02, 24);
+                    std::memcpy(ts.uv0, t.uv0, 16); std::memcpy(ts.uv01, t.uv01, 16); std::memcpy(ts.uv02, t.uv02, 16);
+                    ts.material = p.area_light >= 0 ? (int32_t)d->n_materials : p.material;
+                    ts.area_light = p.area_light;
+                }
+            };
+            for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t);
+            work(0);
+            for (auto& th : pool) th.join();
+        }
+    });
+    struct JoinGuard { std::thread& th; ~JoinGuard() { if (th.joinable()) th.join(); } } shading_guard{shading_records};
     build_reference_bvh(*d, ref, 0, device);
     if (!ref.error.empty()) { set_error(ref.error); return CRAY_E_BVH; }
     if (build_flags & CRAY_BUILD_FAST) {
@@ -270,29 +299,7 @@ int build_host_side(const cray_scene_desc* d, uint32_t build_flags, HostBuild& h
     std::vector<DiskXf>& disks = hb.disks;
     disks.resize(d->n_disks);
     for (size_t i = 0; i < disks.size(); ++i) disks[i] = make_disk(d->disks[i]);
-    // per-primitive shading records for triangles (flat ones are flagged in their LeafPrim, see make_leaf_prim)
-    std::vector<TriShade>& tri_shade = hb.tri_shade;
-    tri_shade.resize(d->n_triangles ? np : 0);
-    {
-        const unsigned nt = std::max(1u, std::thread::hardware_concurrency());
-        std::vector<std::thread> pool;
-        auto work = [&](unsigned t0) {
-            for (size_t i = t0; i < tri_shade.size(); i += nt) {
-                const cray_primitive_desc& p = d->primitives[i];
-                TriShade& ts = tri_shade[i];
-                std::memset(&ts, 0, sizeof(ts));
-                if (p.shape_kind != CRAY_SHAPE_TRIANGLE) continue;
-                const cray_triangle_desc& t = d->triangles[p.shape_index];
-                std::memcpy(ts.n0, t.n0, 24); std::memcpy(ts.n01, t.n01, 24); std::memcpy(ts.n02, t.n02, 24);
-                std::memcpy(ts.uv0, t.uv0, 16); std::memcpy(ts.uv01, t.uv01, 16); std::memcpy(ts.uv02, t.uv02, 16);
-                ts.material = p.area_light >= 0 ? (int32_t)d->n_materials : p.material;
-                ts.area_light = p.area_light;
-            }
-        };
-        for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t);
-        work(0);
-        for (auto& th : pool) th.join();
-    }
+    shading_records.join();   // (built while the tree was)
     timer.mark("shading records");
     // materials (+ the black matte that area-light primitives carry, primitive.rs:43-46)
     std::vector<DevMaterial>& materials = hb.materials;
