@@ -664,71 +664,80 @@ constexpr uint32_t kShadeThreads = CRAY_SHADE_THREADS;
 constexpr uint32_t kShadeKeys = 16;   // class (matte, glass, plastic, metal) x shape kind (3); 12 = miss; 13 = no path
 constexpr uint32_t kKeyMiss = 12u, kKeyNone = 13u;
 
+#ifndef CRAY_CLASSIFY_ITEMS
+#define CRAY_CLASSIFY_ITEMS 4
+#endif
+constexpr uint32_t kClassifyItems = CRAY_CLASSIFY_ITEMS, kClassifyBlock = kShadeThreads * kClassifyItems;   // queue entries per thread / block
+
 __global__ void __launch_bounds__(kShadeThreads) k_shade_classify(const __grid_constant__ SceneView s, const __grid_constant__ Pool p, const __grid_constant__ Job job, Counters* counters) {
-    constexpr uint32_t kWarps = kShadeThreads / 32, kCells = kShadeKeys * kWarps;  // 128 (key, warp) cells
-    __shared__ uint32_t s_count[kCells];
-    __shared__ uint32_t s_warp_total[kCells / 32];
-    __shared__ uint32_t s_order[kShadeThreads];
-    __shared__ uint8_t s_key[kShadeThreads];
+    // cells in (key, round, warp) order: within a key the block's entries keep their queue order
+    constexpr uint32_t kWarps = kShadeThreads / 32, kRows = kClassifyItems * kWarps, kCells = kShadeKeys * kRows;
+    static_assert(kCells == 2 * kShadeThreads, "two cells per thread in the scan");
+    __shared__ uint32_t s_cell[kCells];
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_order[kClassifyBlock];
+    __shared__ uint8_t s_key[kClassifyBlock];
     __shared__ uint32_t s_start[kShadeKeys + 1];
     __shared__ unsigned long long s_base[kShadeKeys];
     // the iteration's rays: the wide traversal's (front of the queue), then the reference-order traversal's (back of it)
     const uint64_t n_front = counters->n_extend;
     const uint64_t n_extend = n_front + counters->n_extend_contact;
-    if ((uint64_t)blockIdx.x * kShadeThreads >= n_extend) return;  // whole block idle
-    const uint64_t q = (uint64_t)blockIdx.x * kShadeThreads + threadIdx.x;
+    const uint64_t block_base = (uint64_t)blockIdx.x * kClassifyBlock;
+    if (block_base >= n_extend) return;  // whole block idle
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t mine = 0xFFFFFFFFu, key = kKeyNone;
-    if (q < n_extend) {
-        mine = p.extend_queue[q < n_front ? (uint32_t)q : p.capacity - 1u - (uint32_t)(q - n_front)];
-        const uint32_t my_slot = p.hit_slot[mine];
-        key = kKeyMiss;
-        if (my_slot != CRAY_NO_HIT) {
-            const LeafPrim* rec = (job.exact ? s.bin_prims : s.wide_prims) + my_slot;
-            const uint32_t kind = __ldg(&rec->kind);
-            key = ((kind >> 8) & 3u) * 3u + (kind & 3u);
-        }
-    }
-    if (threadIdx.x < kCells) s_count[threadIdx.x] = 0u;
-    __syncthreads();
-    const unsigned grp = __match_any_sync(0xFFFFFFFFu, key);
-    if (lane == (unsigned)(__ffs(grp) - 1)) s_count[key * kWarps + warp] = __popc(grp);
-    __syncthreads();
-    // exclusive scan of the cells in (key, warp) order: the first kCells / 32 warps scan 32 cells each
-    uint32_t cell = 0, incl = 0;
-    if (threadIdx.x < kCells) {
-        cell = s_count[threadIdx.x];
-        incl = cell;
+    uint32_t mine[kClassifyItems], key[kClassifyItems], within[kClassifyItems];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= (unsigned)d) incl += up;
+    for (uint32_t r = 0; r < kClassifyItems; ++r) {
+        const uint64_t q = block_base + r * kShadeThreads + threadIdx.x;
+        mine[r] = 0xFFFFFFFFu; key[r] = kKeyNone;
+        if (q < n_extend) {
+            mine[r] = p.extend_queue[q < n_front ? (uint32_t)q : p.capacity - 1u - (uint32_t)(q - n_front)];
+            const uint32_t my_slot = p.hit_slot[mine[r]];
+            key[r] = kKeyMiss;
+            if (my_slot != CRAY_NO_HIT) {
+                const LeafPrim* rec = (job.exact ? s.bin_prims : s.wide_prims) + my_slot;
+                const uint32_t kind = __ldg(&rec->kind);
+                key[r] = ((kind >> 8) & 3u) * 3u + (kind & 3u);
+            }
         }
-        if (lane == 31u) s_warp_total[warp] = incl;
+    }
+    s_cell[2u * threadIdx.x] = 0u; s_cell[2u * threadIdx.x + 1u] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (uint32_t r = 0; r < kClassifyItems; ++r) {
+        const unsigned grp = __match_any_sync(0xFFFFFFFFu, key[r]);
+        if (lane == (unsigned)(__ffs(grp) - 1)) s_cell[key[r] * kRows + r * kWarps + warp] = __popc(grp);
+        within[r] = __popc(grp & ((1u << lane) - 1u));
     }
     __syncthreads();
-    if (threadIdx.x < kCells) {
-        uint32_t before = 0;
-        for (uint32_t w = 0; w < warp; ++w) before += s_warp_total[w];
-        const uint32_t excl = before + incl - cell;
-        s_count[threadIdx.x] = excl;
-        if (threadIdx.x % kWarps == 0u) s_start[threadIdx.x / kWarps] = excl;   // first entry of each key in the sorted block
+    {   // exclusive scan of the cells: two per thread
+        const uint32_t c0 = s_cell[2u * threadIdx.x], c1 = s_cell[2u * threadIdx.x + 1u];
+        uint32_t total;
+        const uint32_t excl = block_scan_256(c0 + c1, s_warp, total);
+        s_cell[2u * threadIdx.x] = excl; s_cell[2u * threadIdx.x + 1u] = excl + c0;
     }
-    if (threadIdx.x == 0) s_start[kShadeKeys] = kShadeThreads;
     __syncthreads();
-    {
-        const uint32_t pos = s_count[key * kWarps + warp] + __popc(grp & ((1u << lane) - 1u));
-        s_order[pos] = mine;
-        s_key[pos] = (uint8_t)key;
+    if (threadIdx.x < kShadeKeys) s_start[threadIdx.x] = s_cell[threadIdx.x * kRows];   // first entry of each key in the sorted block
+    if (threadIdx.x == 0) s_start[kShadeKeys] = kClassifyBlock;
+#pragma unroll
+    for (uint32_t r = 0; r < kClassifyItems; ++r) {
+        const uint32_t pos = s_cell[key[r] * kRows + r * kWarps + warp] + within[r];
+        s_order[pos] = mine[r];
+        s_key[pos] = (uint8_t)key[r];
     }
+    __syncthreads();
     // one atomic per key claims the block's range in that key's queue
     if (threadIdx.x < kKeyNone) {
         const uint32_t cnt = s_start[threadIdx.x + 1] - s_start[threadIdx.x];
         s_base[threadIdx.x] = cnt ? atomicAdd(&counters->class_count[threadIdx.x], (unsigned long long)cnt) : 0ull;
     }
     __syncthreads();
-    const uint32_t k = s_key[threadIdx.x];
-    if (k < kKeyNone) p.class_queue[(uint64_t)k * p.capacity + s_base[k] + (threadIdx.x - s_start[k])] = s_order[threadIdx.x];
+#pragma unroll
+    for (uint32_t r = 0; r < kClassifyItems; ++r) {
+        const uint32_t pos = r * kShadeThreads + threadIdx.x;
+        const uint32_t k = s_key[pos];
+        if (k < kKeyNone) p.class_queue[(uint64_t)k * p.capacity + s_base[k] + (pos - s_start[k])] = s_order[pos];
+    }
 }
 
 // One path vertex on a primitive of shade class CLS.
@@ -1002,6 +1011,7 @@ int resident_blocks(Kernel kernel, int* per_sm) {
     return CRAY_OK;
 }
 
+constexpr int kPoolNoMemory = -100;   // (internal) the device could not hold a pool of the requested capacity
 int ensure_pool(cray_scene* sc, uint32_t capacity) {
     auto* ps = static_cast<PoolStorage*>(sc->pool);
     if (!ps) { ps = new PoolStorage(); sc->pool = ps; }
@@ -1036,7 +1046,13 @@ int ensure_pool(cray_scene* sc, uint32_t capacity) {
     const size_t n = capacity;
     const size_t n_f64 = 21, n_u32 = 8 + 13;  // (+ the 13 queues of the shade stage)
     const size_t bytes = n * (n_f64 * 8 + n_u32 * 4);
-    CRAY_CUDA(cudaMalloc(&ps->slab, bytes));
+    if (cudaMalloc(&ps->slab, bytes) != cudaSuccess) {   // the caller retries with a smaller pool
+        cudaGetLastError();
+        ps->slab = nullptr;
+        ps->pool.capacity = 0;
+        if (capacity <= (1u << 20)) { set_error("out of device memory for the path pool"); return CRAY_E_CUDA; }
+        return kPoolNoMemory;
+    }
     // cleared before anyone can touch it, whichever stream the caller renders on
     CRAY_CUDA(cudaMemsetAsync(ps->slab, 0, bytes, sc->stream));
     CRAY_CUDA(cudaStreamSynchronize(sc->stream));
@@ -1058,6 +1074,11 @@ int ensure_pool(cray_scene* sc, uint32_t capacity) {
 // Runs the wavefront until every sample of `job` has been flushed.
 int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t stream, cray_render_stats* stats) {
     int rc = ensure_pool(sc, capacity);
+    while (rc == kPoolNoMemory && capacity > (1u << 20)) {   // a device short of memory renders with fewer paths in flight
+        capacity = (capacity + 1u) / 2u;
+        rc = ensure_pool(sc, capacity);
+    }
+    if (rc == kPoolNoMemory) { set_error("out of device memory for the path pool"); return CRAY_E_CUDA; }
     if (rc != CRAY_OK) return rc;
     auto* ps = static_cast<PoolStorage*>(sc->pool);
     Pool pool = ps->pool;
@@ -1105,7 +1126,7 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
         {
             const unsigned blocks = (capacity + kShadeThreads - 1) / kShadeThreads;
             const unsigned strided = std::min(blocks, ps->shade_blocks);   // the class kernels walk their queues with a grid stride
-            k_shade_classify<<<blocks, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
+            k_shade_classify<<<(capacity + kClassifyBlock - 1) / kClassifyBlock, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
             k_shade_class<CRAY_MAT_METAL><<<strided, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
             k_shade_class<CRAY_MAT_MATTE><<<strided, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
             k_shade_class<CRAY_MAT_PLASTIC><<<strided, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
@@ -1374,10 +1395,12 @@ int cray_render_device(cray_scene* sc, int mode, uint64_t seed, uint32_t sample_
         job.sobol = sc->d_sobol;
         job.exact = mode == CRAY_TRAVERSE_EXACT;
         job.f32 = mode == CRAY_TRAVERSE_F32;
-        // path slots in flight: up to 2^26 (17 GB of path state and queues of the 180 GB; measured 2^22 .. 2^26, profiles/r2d_pool_sweep.txt:
-        // longer launches amortise the tails of the persistent traversal kernels); CRAY_POOL_LOG2 overrides it for tuning
-        uint32_t pool_log2 = 26;
-        if (const char* e = std::getenv("CRAY_POOL_LOG2")) pool_log2 = (uint32_t)std::max(10, std::min(26, std::atoi(e)));
+        // path slots in flight: up to 2^28 (252 B of path state and queues per slot: a third of the 180 GB for the 245.8 M samples of the
+        // headline frame, which then is ONE wave -- every launch as long as it can be, the tails of the persistent traversal kernels
+        // amortised; measured 2^22 .. 2^28, profiles/r2d_pool_sweep.txt; a device short of memory gets a smaller pool, run_wavefront);
+        // CRAY_POOL_LOG2 overrides it for tuning
+        uint32_t pool_log2 = 28;
+        if (const char* e = std::getenv("CRAY_POOL_LOG2")) pool_log2 = (uint32_t)std::max(10, std::min(28, std::atoi(e)));
         const uint32_t capacity = (uint32_t)std::min<uint64_t>(n_total, 1ull << pool_log2);
         rc = run_wavefront(sc, job, capacity, stream, stats);
         if (rc != CRAY_OK) return rc;
