@@ -79,17 +79,21 @@ def source_sha256():
     return h.hexdigest()
 
 
-def profiled_traffic():
-    """DRAM bytes per launch of each kernel from the committed `ncu --set full` capture of this workload (tools/final_capture.sh
-    -> tools/kernel_traffic.py -> profiles/kernel_traffic.json).  The capture names the sources of the library it was taken on by
-    sha256: if the library being timed now is built from other sources, the figures are not this code's and nothing is reported
-    (null).  CRAY_B200_LIB (a tuning variant) never matches."""
+def profiled_traffic(args=None, world=1):
+    """DRAM bytes of each kernel from the committed ncu launch list of this workload (tools/final_capture.sh ->
+    tools/kernel_traffic.py -> profiles/kernel_traffic.json): per render (= one bench step), per launch (the mean over the
+    render's launches, one per bounce) and per ray.  The capture names the sources of the library it was taken on by sha256 and
+    the workload (spp, film, triangles): if the library being timed now is built from other sources, or this run renders
+    something else, the figures are not this run's and nothing is reported (null).  CRAY_B200_LIB (a tuning variant) never matches."""
     try:
         if os.environ.get("CRAY_B200_LIB"):
             return None
         with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
             data = json.load(f)
         if data.get("source_sha256") != source_sha256():
+            return None
+        w = data.get("workload", {})
+        if args is not None and (world != 1 or (w.get("spp"), w.get("width"), w.get("height"), w.get("triangles")) != (args.spp, args.width, args.height, args.triangles)):
             return None
         return data
     except Exception:
@@ -246,7 +250,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "Mrays/s on dragon.cry", "value": value, "unit": "Mrays/s",
             "value_counts": "reference rays = Scene::intersect + Scene::intersects calls (every one of them is traced by the CPU renderer)", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "spp": args.spp, "max_depth": 8, "sampler": "sobol"},
+            "data": "synthetic", "config": {"workload": WORKLOAD, "spp": args.spp, "film": [args.width, args.height], "max_depth": 8, "sampler": "sobol"},
             "samples_per_s": args.width * args.height * spp * args.steps / dt,
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -373,7 +377,7 @@ def run_ours(args):
         extend_ms = totals["trace_ms"]
         bytes_per_ray = ALGORITHMIC_BYTES_PER_RAY_F32 if args.mode == "f32" else ALGORITHMIC_BYTES_PER_RAY
         achieved = totals["closest"] * bytes_per_ray / (extend_ms * 1e-3) / 1e9 if extend_ms > 0 else 0.0
-        traffic = profiled_traffic() if args.mode == "fast" else None
+        traffic = profiled_traffic(args, world) if args.mode == "fast" else None
         tk = (traffic or {}).get("kernels", {})
 
         def other(kernel, units, unit_name, per_unit, ms, key):
@@ -381,12 +385,13 @@ def run_ours(args):
             t = tk.get(key)
             return {"kernel": kernel, "bound": "hbm", "achieved": got, "peak": peak, "unit": "GB/s", "frac": got / peak, "units": units, "unit_name": unit_name,
                     "algorithmic_bytes_per_unit": per_unit, "kernel_ms": ms, "kernel_share_of_step": ms / max(totals["render_ms"], 1e-9),
+                    "launches": totals["iters"], "algorithmic_bytes_per_launch": units * per_unit / max(totals["iters"], 1),
                     "traffic": t["dram_bytes_per_launch"] if t else None, "traffic_detail": t}
 
         line = {
             "metric": "Mrays/s on dragon.cry", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "spp": args.spp, "max_depth": 8, "sampler": "sobol", "traversal": args.mode, "parallelism": f"samples/{world}",
+            "config": {"workload": WORKLOAD, "spp": args.spp, "film": [args.width, args.height], "max_depth": 8, "sampler": "sobol", "traversal": args.mode, "parallelism": f"samples/{world}",
                        "l2": "per-step working set (triangle records 578 MB + 8-wide nodes 115 MB + shading records 924 MB) exceeds the 126 MB L2"},
             "value_counts": "reference rays = Scene::intersect + Scene::intersects calls of the reference for the same samples (the CPU arm counts the same)",
             "rays": {"reference_closest": counts_dev[0], "reference_shadow": counts_dev[1], "traced_shadow": counts_dev[3],
@@ -403,6 +408,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_wide_persistent<false, ExtendSource" + (", true" if args.mode == "f32" else "") + "> (closest-hit traversal, 8-wide BVH)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_kind, "algorithmic_bytes_per_ray": bytes_per_ray,
                          "rays_in_kernel": totals["closest"], "kernel_ms": extend_ms, "kernel_share_of_step": extend_ms / max(totals["render_ms"], 1e-9),
+                         "launches": totals["iters"], "algorithmic_bytes_per_launch": totals["closest"] * bytes_per_ray / max(totals["iters"], 1),
                          "traffic": tk["extend"]["dram_bytes_per_launch"] if "extend" in tk else None, "traffic_detail": tk.get("extend"),
                          "traffic_capture": {k: v for k, v in (traffic or {}).items() if k != "kernels"} or None},
             "other_kernels": [
@@ -468,7 +474,7 @@ def run_single_process(args):
     emit({"metric": "Mrays/s on dragon.cry", "value": rays / device_ms / 1e3, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
           "ms_per_step": device_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
           "launch": "single process: cray_scene_create_multi + cray_render_multi (include/cray_b200.h)",
-          "config": {"workload": WORKLOAD, "spp": args.spp, "max_depth": 8, "sampler": "sobol", "traversal": args.mode, "parallelism": f"samples/{args.gpus}"},
+          "config": {"workload": WORKLOAD, "spp": args.spp, "film": [args.width, args.height], "max_depth": 8, "sampler": "sobol", "traversal": args.mode, "parallelism": f"samples/{args.gpus}"},
           "value_counts": "reference rays = Scene::intersect + Scene::intersects calls of the reference for the same samples",
           "rays": {"reference_mrays_per_s": rays / device_ms / 1e3, "traced_mrays_per_s": traced / device_ms / 1e3},
           "samples_per_s": samples / (device_ms * 1e-3),
