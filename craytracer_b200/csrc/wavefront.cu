@@ -49,6 +49,9 @@ struct Pool {  // structure-of-arrays over `capacity` path slots
     // front; rays that start in a contact shell (state bit 19, fast and F32 modes) go to the reference-order traversal and fill the
     // same array from the back (entry k at capacity - 1 - k): the two never meet, there is at most one entry per slot.
     uint32_t *extend_queue, *shadow_queue;
+    // the previous iteration's extend queue (the two arrays swap every iteration): once every sample has been generated, the next
+    // queue is the survivors of this one (k_requeue) and nobody scans the whole pool any more
+    uint32_t* extend_queue_prev;
     // the shade stage's queues: kKeyNone arrays of `capacity` entries, one per (shade class, shape kind) key and one for the misses
     uint32_t* class_queue;
 };
@@ -60,7 +63,10 @@ struct Job {
     uint64_t n_total;           // samples in this job
     uint32_t sample_begin;
     uint32_t n_pixels;
-    const uint32_t* pixel_order;  // full frame: id -> sample sample_begin + id / n_pixels of pixel pixel_order[id % n_pixels]
+    // full frame: the samples of the job are taken `sample_group` at a time -- ids run over the samples of a group fastest, then
+    // over the pixels (in pixel_order), then over the groups; the last group may be shorter
+    const uint32_t* pixel_order;
+    uint32_t n_samples, sample_group;
     const uint32_t *lx, *ly, *ls; // explicit list (S2), or null
     double* film;               // W*H*3 f64 sums, or null
     double* out_rgb;            // per-sample radiance (S2), or null
@@ -572,9 +578,12 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneV
         uint32_t x, y, si;
         if (job.lx) { x = job.lx[id]; y = job.ly[id]; si = job.ls[id]; }
         else {
-            const uint32_t po = job.pixel_order[id % job.n_pixels];
+            const unsigned long long pass = (unsigned long long)job.n_pixels * job.sample_group;
+            const uint32_t group = (uint32_t)(id / pass), rem = (uint32_t)(id % pass);
+            const uint32_t in_group = min(job.sample_group, job.n_samples - group * job.sample_group);
+            const uint32_t po = job.pixel_order[rem / in_group];
             x = po & 0xFFFFu; y = po >> 16;
-            si = job.sample_begin + (uint32_t)(id / job.n_pixels);
+            si = job.sample_begin + group * job.sample_group + rem % in_group;
         }
         PixelSampler smp;
         smp.start_pixel(job.seed, x, y, si);
@@ -620,6 +629,43 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SceneV
     for (uint32_t k = 0; k < kGenSlots; ++k) {
         if (contact_mask & (1u << k)) p.extend_queue[p.capacity - 1u - (uint32_t)(s_base[2] + crank++)] = first + k;
         else if (live_mask & (1u << k)) p.extend_queue[s_base[1] + qrank++] = first + k;
+    }
+}
+
+// k_generate's stand-in once the job has no samples left to start: the iteration's extend queue = the slots of the previous
+// one whose path is still alive, in the same order, found by walking that queue (n_front entries at its front, n_contact at its
+// back) instead of the whole pool -- by then most slots are empty and stay so.  (A path that ended waiting for its shadow ray
+// was flushed by the shadow kernel; one still found DONE is flushed here, as in k_generate.)
+__global__ void __launch_bounds__(256) k_requeue(const __grid_constant__ Pool p, const __grid_constant__ Job job, Counters* counters, uint64_t n_front, uint64_t n_contact) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ unsigned long long s_base[2];
+    const uint64_t first = ((uint64_t)blockIdx.x * 256u + threadIdx.x) * kGenSlots, n_prev = n_front + n_contact;
+    uint32_t slot[kGenSlots];
+    uint32_t live_mask = 0, contact_mask = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kGenSlots; ++k) {
+        const uint64_t q = first + k;
+        if (q >= n_prev) break;
+        const uint32_t i = p.extend_queue_prev[q < n_front ? (uint32_t)q : p.capacity - 1u - (uint32_t)(q - n_front)];
+        const uint32_t st = p.state[i];
+        slot[k] = i;
+        if (st_state(st) == SLOT_DONE) flush_path(p, job, counters, i, p.L_r[i], p.L_g[i], p.L_b[i], (st >> 18) & 1u);
+        else if (st_state(st) == SLOT_ACTIVE) {
+            if (st & kStateContact) contact_mask |= 1u << k;
+            else live_mask |= 1u << k;
+        }
+    }
+    uint32_t totals;
+    const uint32_t ranks = block_scan_256(__popc(live_mask) | (__popc(contact_mask) << 16), s_warp, totals);
+    const uint32_t n_wide = totals & 0xFFFFu, n_back = totals >> 16;
+    if (threadIdx.x == 0 && n_wide) s_base[0] = atomicAdd(&counters->n_extend, (unsigned long long)n_wide);
+    if (threadIdx.x == 32 && n_back) s_base[1] = atomicAdd(&counters->n_extend_contact, (unsigned long long)n_back);
+    __syncthreads();
+    uint32_t qrank = ranks & 0xFFFFu, crank = ranks >> 16;
+#pragma unroll
+    for (uint32_t k = 0; k < kGenSlots; ++k) {
+        if (contact_mask & (1u << k)) p.extend_queue[p.capacity - 1u - (uint32_t)(s_base[1] + crank++)] = slot[k];
+        else if (live_mask & (1u << k)) p.extend_queue[s_base[0] + qrank++] = slot[k];
     }
 }
 
@@ -1044,7 +1090,7 @@ int ensure_pool(cray_scene* sc, uint32_t capacity) {
     if (ps->pool.capacity >= capacity) return CRAY_OK;
     if (ps->slab) { cudaDeviceSynchronize(); cudaFree(ps->slab); ps->slab = nullptr; }  // (re-)allocation is rare: grow only
     const size_t n = capacity;
-    const size_t n_f64 = 21, n_u32 = 8 + 13;  // (+ the 13 queues of the shade stage)
+    const size_t n_f64 = 21, n_u32 = 9 + 13;  // (+ the 13 queues of the shade stage)
     const size_t bytes = n * (n_f64 * 8 + n_u32 * 4);
     if (cudaMalloc(&ps->slab, bytes) != cudaSuccess) {   // the caller retries with a smaller pool
         cudaGetLastError();
@@ -1063,7 +1109,7 @@ int ensure_pool(cray_scene* sc, uint32_t capacity) {
     size_t k = 0;
     for (double** fp : fields) { *fp = f + k * n; ++k; }
     uint32_t* u = reinterpret_cast<uint32_t*>(f + n_f64 * n);
-    uint32_t** ufields[] = {&p.hit_slot, &p.id, &p.pixel, &p.hash, &p.shuffled_rev, &p.state, &p.extend_queue, &p.shadow_queue};
+    uint32_t** ufields[] = {&p.hit_slot, &p.id, &p.pixel, &p.hash, &p.shuffled_rev, &p.state, &p.extend_queue, &p.extend_queue_prev, &p.shadow_queue};
     k = 0;
     for (uint32_t** up : ufields) { *up = u + k * n; ++k; }
     p.class_queue = u + k * n;
@@ -1099,6 +1145,9 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
     // fast mode: rays that start in a contact shell go to the reference-order kernels (only scenes with marked primitives have any)
     const bool contact = !job.exact && sc->info.contact_primitives > 0;
     uint64_t iterations = 0, launches = 0, closest = 0;
+    // once every sample of the job has been started (known from the counters of the previous iteration), k_requeue replaces k_generate
+    bool exhausted = false;
+    uint64_t prev_front = 0, prev_contact = 0;
     const bool timed = stats != nullptr;
     // The host never waits for traversal or shading: it enqueues the whole iteration, then waits only for the iteration's
     // k_generate (long finished by the time the GPU works through extend / shade / shadow) to learn whether any path is
@@ -1114,7 +1163,9 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
             CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter], stream));
         }
         k_begin_iteration<<<1, 1, 0, stream>>>(dc);
-        k_generate<<<g256, 256, 0, stream>>>(sc->view, pool, job, dc);
+        std::swap(pool.extend_queue, pool.extend_queue_prev);
+        if (!exhausted) k_generate<<<g256, 256, 0, stream>>>(sc->view, pool, job, dc);
+        else k_requeue<<<(unsigned)((prev_front + prev_contact + kGenBlock - 1) / kGenBlock), 256, 0, stream>>>(pool, job, dc, prev_front, prev_contact);
         CRAY_CUDA(cudaMemcpyAsync(ps->h_counters, dc, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
         CRAY_CUDA(cudaEventRecord(ev.gen_done, stream));
         if (timed) CRAY_CUDA(cudaEventRecord(ps->timers[kMarks * iter + 1], stream));
@@ -1126,7 +1177,9 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
         {
             const unsigned blocks = (capacity + kShadeThreads - 1) / kShadeThreads;
             const unsigned strided = std::min(blocks, ps->shade_blocks);   // the class kernels walk their queues with a grid stride
-            k_shade_classify<<<(capacity + kClassifyBlock - 1) / kClassifyBlock, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
+            // (the queue's length lives on the device; it cannot exceed the previous iteration's once no new paths start)
+            const uint64_t most = exhausted ? prev_front + prev_contact : capacity;
+            k_shade_classify<<<(unsigned)((most + kClassifyBlock - 1) / kClassifyBlock), kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
             k_shade_class<CRAY_MAT_METAL><<<strided, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
             k_shade_class<CRAY_MAT_MATTE><<<strided, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
             k_shade_class<CRAY_MAT_PLASTIC><<<strided, kShadeThreads, 0, stream>>>(sc->view, pool, job, dc);
@@ -1146,6 +1199,8 @@ int run_wavefront(cray_scene* sc, Job job, uint32_t capacity, cudaStream_t strea
         CRAY_CUDA(cudaEventSynchronize(ev.gen_done));
         const uint64_t live = ps->h_counters->n_extend + ps->h_counters->n_extend_contact;
         if (live == 0) break;
+        prev_front = ps->h_counters->n_extend; prev_contact = ps->h_counters->n_extend_contact;
+        exhausted = ps->h_counters->next_id >= job.n_total;
         closest += live;
         iterations += 1;
     }
@@ -1391,11 +1446,15 @@ int cray_render_device(cray_scene* sc, int mode, uint64_t seed, uint32_t sample_
         job.sample_begin = sample_begin;
         job.n_pixels = (uint32_t)n_pixels;
         job.pixel_order = sc->d_pixel_order;
+        job.n_samples = sample_end - sample_begin;
+        job.sample_group = job.n_samples;   // default: all samples of a pixel together
+        if (const char* e = std::getenv("CRAY_SAMPLE_GROUP")) job.sample_group = (uint32_t)std::max(1, std::atoi(e));
+        job.sample_group = std::min(job.sample_group, job.n_samples);
         job.film = ps->d_film;
         job.sobol = sc->d_sobol;
         job.exact = mode == CRAY_TRAVERSE_EXACT;
         job.f32 = mode == CRAY_TRAVERSE_F32;
-        // path slots in flight: up to 2^28 (252 B of path state and queues per slot: a third of the 180 GB for the 245.8 M samples of the
+        // path slots in flight: up to 2^28 (256 B of path state and queues per slot: a third of the 180 GB for the 245.8 M samples of the
         // headline frame, which then is ONE wave -- every launch as long as it can be, the tails of the persistent traversal kernels
         // amortised; measured 2^22 .. 2^28, profiles/r2d_pool_sweep.txt; a device short of memory gets a smaller pool, run_wavefront);
         // CRAY_POOL_LOG2 overrides it for tuning
