@@ -983,17 +983,17 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_miss(const __grid_const
         const bool is_specular_bounce = (st >> 16) & 1u;
         const bool bad = (st >> 18) & 1u;
         Color3 L = mkc(p.L_r[i], p.L_g[i], p.L_b[i]);
-        const Color3 beta = mkc(p.beta_r[i], p.beta_g[i], p.beta_b[i]);
-        const double prev_bsdf_pdf = p.prev_bsdf_pdf[i];
         for (uint32_t li = 0; li < s.n_lights; ++li) {
             const DevLight& light = s.lights[li];
             if (light.kind != CRAY_LIGHT_INFINITE) continue;  // Light::Le is black for every other kind (light.rs:161-168)
+            // (throughput and pdf are read only here: a scene without an infinite light flushes its escaped paths from L alone)
+            const Color3 beta = mkc(p.beta_r[i], p.beta_g[i], p.beta_b[i]);
             const Color3 Le = mkc(light.color[0], light.color[1], light.color[2]);
             if (is_specular_bounce) {
                 L = L + beta * Le;
             } else if (!is_black(Le)) {
                 const double light_pdf = (kFrac1Pi / 4.0) * light_pick_pdf(s, li);
-                const double weight = power_heuristic(light_pdf, prev_bsdf_pdf);
+                const double weight = power_heuristic(light_pdf, p.prev_bsdf_pdf[i]);
                 L = L + beta * Le * weight;
             }
         }
