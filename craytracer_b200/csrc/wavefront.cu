@@ -974,30 +974,63 @@ __global__ void __launch_bounds__(kShadeThreads, shade_blocks_of_class(CLS)) k_s
     }
 }
 
-// The paths that left the scene (path_integrator.rs:60-90).
+// The paths that left the scene (path_integrator.rs:60-90).  Paths start pixel by pixel, so the lanes of a warp mostly end on the
+// same pixel: the radiances of each run of lanes on one pixel are summed in the warp first, and the run gets one set of film
+// atomics instead of up to 32 on the same three addresses (the order of the f64 film sums is free either way).
 __global__ void __launch_bounds__(kShadeThreads) k_shade_miss(const __grid_constant__ SceneView s, const __grid_constant__ Pool p, const __grid_constant__ Job job, Counters* counters) {
     const uint64_t n = counters->class_count[kKeyMiss];
-    for (uint64_t t = (uint64_t)blockIdx.x * kShadeThreads + threadIdx.x; t < n; t += (uint64_t)gridDim.x * kShadeThreads) {
-        const uint32_t i = p.class_queue[(uint64_t)kKeyMiss * p.capacity + t];
-        const uint32_t st = p.state[i];
-        const bool is_specular_bounce = (st >> 16) & 1u;
-        const bool bad = (st >> 18) & 1u;
-        Color3 L = mkc(p.L_r[i], p.L_g[i], p.L_b[i]);
-        for (uint32_t li = 0; li < s.n_lights; ++li) {
-            const DevLight& light = s.lights[li];
-            if (light.kind != CRAY_LIGHT_INFINITE) continue;  // Light::Le is black for every other kind (light.rs:161-168)
-            // (throughput and pdf are read only here: a scene without an infinite light flushes its escaped paths from L alone)
-            const Color3 beta = mkc(p.beta_r[i], p.beta_g[i], p.beta_b[i]);
-            const Color3 Le = mkc(light.color[0], light.color[1], light.color[2]);
-            if (is_specular_bounce) {
-                L = L + beta * Le;
-            } else if (!is_black(Le)) {
-                const double light_pdf = (kFrac1Pi / 4.0) * light_pick_pdf(s, li);
-                const double weight = power_heuristic(light_pdf, p.prev_bsdf_pdf[i]);
-                L = L + beta * Le * weight;
+    const unsigned lane = threadIdx.x & 31u;
+    for (uint64_t base = (uint64_t)blockIdx.x * kShadeThreads + (threadIdx.x & ~31u); base < n; base += (uint64_t)gridDim.x * kShadeThreads) {
+        const uint64_t t = base + lane;
+        const bool valid = t < n;
+        uint32_t i = 0, pixel = 0xFFFFFFFFu;
+        Color3 L = mkc(0.0, 0.0, 0.0);
+        bool good = false;
+        if (valid) {
+            i = p.class_queue[(uint64_t)kKeyMiss * p.capacity + t];
+            const uint32_t st = p.state[i];
+            const bool is_specular_bounce = (st >> 16) & 1u;
+            const bool bad = (st >> 18) & 1u;
+            L = mkc(p.L_r[i], p.L_g[i], p.L_b[i]);
+            for (uint32_t li = 0; li < s.n_lights; ++li) {
+                const DevLight& light = s.lights[li];
+                if (light.kind != CRAY_LIGHT_INFINITE) continue;  // Light::Le is black for every other kind (light.rs:161-168)
+                // (throughput and pdf are read only here: a scene without an infinite light flushes its escaped paths from L alone)
+                const Color3 beta = mkc(p.beta_r[i], p.beta_g[i], p.beta_b[i]);
+                const Color3 Le = mkc(light.color[0], light.color[1], light.color[2]);
+                if (is_specular_bounce) {
+                    L = L + beta * Le;
+                } else if (!is_black(Le)) {
+                    const double light_pdf = (kFrac1Pi / 4.0) * light_pick_pdf(s, li);
+                    const double weight = power_heuristic(light_pdf, p.prev_bsdf_pdf[i]);
+                    L = L + beta * Le * weight;
+                }
+            }
+            good = !bad && is_finite3(L);
+            if (!job.film || job.out_rgb || !good) {   // per-sample output, or a dropped sample: the plain way
+                flush_path(p, job, counters, i, L.r, L.g, L.b, bad);
+                good = false;
+            } else {
+                pixel = p.pixel[i];
+                p.state[i] = SLOT_EMPTY;
             }
         }
-        flush_path(p, job, counters, i, L.r, L.g, L.b, bad);
+        // runs of neighbouring lanes on the same pixel: a segmented sum over each run, its first lane adds it to the film
+        const uint32_t key = good ? pixel : 0xFFFFFFFFu;
+        const uint32_t before = __shfl_up_sync(0xFFFFFFFFu, key, 1);
+        const unsigned heads = __ballot_sync(0xFFFFFFFFu, lane == 0u || key != before);
+        const unsigned later = lane == 31u ? 0u : heads & ~((2u << lane) - 1u);
+        const unsigned run_end = later ? (unsigned)__ffs(later) - 2u : 31u;   // last lane of this lane's run
+        double r = L.r, g = L.g, b = L.b;
+#pragma unroll
+        for (unsigned d = 1; d < 32u; d <<= 1) {
+            const double r2 = __shfl_down_sync(0xFFFFFFFFu, r, d), g2 = __shfl_down_sync(0xFFFFFFFFu, g, d), b2 = __shfl_down_sync(0xFFFFFFFFu, b, d);
+            if (lane + d <= run_end) { r += r2; g += g2; b += b2; }
+        }
+        if (good && ((heads >> lane) & 1u)) {
+            double* px = job.film + 3ull * pixel;
+            atomicAdd(px, r); atomicAdd(px + 1, g); atomicAdd(px + 2, b);
+        }
     }
 }
 

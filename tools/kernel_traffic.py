@@ -25,7 +25,7 @@ import sys
 CLASSES = [("extend", r"k_wide_persistent<(\(bool\))?0, (cray::)?ExtendSource, (\(bool\))?0>"), ("shadow", r"k_wide_persistent<(\(bool\))?1, (cray::)?ShadowSource, (\(bool\))?0>"),
            ("shade_classify", r"k_shade_classify"), ("shade_matte", r"k_shade_class<(\(unsigned int\))?0>"), ("shade_glass", r"k_shade_class<(\(unsigned int\))?1>"),
            ("shade_plastic", r"k_shade_class<(\(unsigned int\))?2>"), ("shade_metal", r"k_shade_class<(\(unsigned int\))?3>"), ("shade_miss", r"k_shade_miss"),
-           ("generate", r"k_generate"), ("begin_iteration", r"k_begin_iteration"), ("extend_f32", r"k_wide_persistent<(\(bool\))?0, (cray::)?ExtendSource, (\(bool\))?1>")]
+           ("generate", r"k_generate"), ("requeue", r"k_requeue"), ("begin_iteration", r"k_begin_iteration"), ("extend_f32", r"k_wide_persistent<(\(bool\))?0, (cray::)?ExtendSource, (\(bool\))?1>")]
 SCALE_B = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 SCALE_MS = {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3, "nsecond": 1e-6}
 RENDERS = 2  # bench.py --steps 1 --warmup 0: the device-film leg and the host-film leg, same seed
