@@ -35,3 +35,32 @@ def test_our_arm_has_no_cpu_path():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + SMALL, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert res.returncode != 0 and res.stdout.strip() == ""
     assert "no CUDA device" in res.stderr
+
+
+def test_traffic_figures_are_reported_only_for_the_code_and_workload_they_were_captured_on(monkeypatch):
+    """roofline.traffic comes from a committed ncu capture (profiles/kernel_traffic.json): it names the kernels' sources by sha256
+    and the workload; anything else gets null rather than another build's figures."""
+    import argparse
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
+        data = json.load(f)
+    w = data["workload"]
+    args = argparse.Namespace(spp=w["spp"], width=w["width"], height=w["height"], triangles=w["triangles"])
+    for key in ("extend", "shadow", "shade"):
+        k = data["kernels"][key]
+        assert k["dram_bytes_per_launch"] * k["launches_per_render"] == k["dram_bytes_per_render"]
+        assert abs(k["dram_bytes_per_unit"] * k["units_per_render"] - k["dram_bytes_per_render"]) <= 1e-6 * k["dram_bytes_per_render"]
+    got = bench.profiled_traffic(args, 1)
+    if data["source_sha256"] == bench.source_sha256():
+        assert got is not None and got["kernels"]["extend"]["dram_bytes_per_launch"] > 0
+    else:
+        assert got is None          # kernels edited since the capture: nothing is claimed until it is retaken
+    args.spp += 1
+    assert bench.profiled_traffic(args, 1) is None
+    args.spp -= 1
+    assert bench.profiled_traffic(args, 2) is None
+    monkeypatch.setenv("CRAY_B200_LIB", "/some/variant.so")
+    assert bench.profiled_traffic(args, 1) is None
