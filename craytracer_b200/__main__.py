@@ -37,6 +37,7 @@ def main(argv=None):
     ap.add_argument("--mode", choices=["fast", "exact", "f32"], default="fast")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--base-dir", default=None, help="directory mesh paths are resolved against")
+    ap.add_argument("--samples-per-call", type=int, default=0, help="split the sample range into render calls of this many samples (default: as many as one call takes)")
     args = ap.parse_args(argv)
 
     start = time.time()
@@ -53,9 +54,18 @@ def main(argv=None):
     spp = args.spp if args.spp is not None else sc0.num_samples
     mode = {"exact": TRAVERSE_EXACT, "fast": TRAVERSE_FAST, "f32": TRAVERSE_F32}[args.mode]
     t0 = time.time()
-    film, st = render_multi(gpu_scenes, seed=args.seed, sample_begin=0, sample_end=spp, mode=mode)
+    # one render call takes at most 2^32 - 1 samples per GPU: a frame with more is rendered as several sample ranges whose sums add up
+    per_call = args.samples_per_call if args.samples_per_call > 0 else max(1, 0xFFFFFFFF // (sc0.width * sc0.height)) * len(gpu_scenes)
+    film, stats, begin = None, [], 0
+    while True:
+        end = min(spp, begin + per_call)
+        part, st = render_multi(gpu_scenes, seed=args.seed, sample_begin=begin, sample_end=end, mode=mode)
+        film = part if film is None else film + part
+        stats.append(st)
+        begin = end
+        if end >= spp:
+            break
     film = film / np.float32(max(spp, 1))  # pixels /= num_samples (craytracer.rs:253-259)
-    stats = [st]
     dt = time.time() - t0
     rays = sum(s.closest_rays + s.shadow_rays for s in stats)          # the reference's Scene::intersect + intersects calls
     traced = sum(s.closest_rays + s.shadow_rays_traced for s in stats)  # rays traced here (a light sample that cannot contribute needs none)

@@ -7,6 +7,7 @@
 // section 2).  Everything goes through the C ABI of include/cray_b200.h -- this file is also the worked example of a host
 // that binds it.  Log lines mimic env_logger's "[INFO] ..." on stderr; a parse error is reported as
 // "<message> at <file>:<line>:<column>" and, like the reference's main, is not a failing exit status.
+#include <algorithm>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -25,13 +26,14 @@ struct Args {
     std::string scene, output = "out.exr", mode = "fast", base_dir;
     uint64_t seed = 0;
     long spp = -1;
+    long samples_per_call = 0;   // 0: as many as one render call takes
     int gpus = 1;
     bool preview = false;
 };
 
 void usage(FILE* f) {
     std::fputs("usage: cray_b200 --scene <file.cry> [--output out.exr] [--seed N] [--preview]\n"
-               "                 [--spp N] [--mode fast|exact|f32] [--gpus N] [--base-dir DIR]\n", f);
+               "                 [--spp N] [--mode fast|exact|f32] [--gpus N] [--base-dir DIR] [--samples-per-call N]\n", f);
 }
 
 bool parse_args(int argc, char** argv, Args& a) {
@@ -51,6 +53,7 @@ bool parse_args(int argc, char** argv, Args& a) {
         else if (k == "--mode") { if (!(v = value("--mode"))) return false; a.mode = v; }
         else if (k == "--gpus") { if (!(v = value("--gpus"))) return false; a.gpus = std::atoi(v); }
         else if (k == "--base-dir") { if (!(v = value("--base-dir"))) return false; a.base_dir = v; }
+        else if (k == "--samples-per-call") { if (!(v = value("--samples-per-call"))) return false; a.samples_per_call = std::strtol(v, nullptr, 10); }
         else { std::fprintf(stderr, "error: unexpected argument '%s'\n", k.c_str()); return false; }
     }
     if (a.scene.empty()) { std::fputs("error: the following required arguments were not provided: --scene <SCENE>\n", stderr); return false; }
@@ -115,8 +118,28 @@ int main(int argc, char** argv) {
     std::vector<float> pixels((size_t)width * height * 3, 0.0f);
     cray_render_stats stats{};
     const auto t_render = std::chrono::steady_clock::now();
-    if (args.gpus == 1) rc = cray_render(scenes[0], mode, args.seed, 0, spp, pixels.data(), &stats);
-    else rc = cray_render_multi(scenes.data(), args.gpus, mode, args.seed, 0, spp, pixels.data(), &stats);
+    // One render call takes at most 2^32 - 1 samples per GPU (and keeps a path slot for each in flight): a frame
+    // with more -- 720x1280 from 4661 spp on one GPU -- is rendered as several sample ranges, whose film sums add up.
+    const uint64_t n_pixels = (uint64_t)width * height;
+    uint64_t per_call = std::max<uint64_t>(1, 0xFFFFFFFFull / std::max<uint64_t>(n_pixels, 1)) * (uint64_t)args.gpus;
+    if (args.samples_per_call > 0) per_call = (uint64_t)args.samples_per_call;
+    std::vector<float> part;
+    for (uint64_t begin = 0;; begin += per_call) {
+        const uint32_t end = (uint32_t)std::min<uint64_t>(spp, begin + per_call);
+        const bool whole = begin == 0 && end == spp;
+        if (!whole && part.empty()) part.resize(pixels.size());
+        float* dst = whole ? pixels.data() : part.data();
+        cray_render_stats st{};
+        if (args.gpus == 1) rc = cray_render(scenes[0], mode, args.seed, (uint32_t)begin, end, dst, &st);
+        else rc = cray_render_multi(scenes.data(), args.gpus, mode, args.seed, (uint32_t)begin, end, dst, &st);
+        if (rc != CRAY_OK) break;
+        if (!whole)
+            for (size_t i = 0; i < pixels.size(); ++i) pixels[i] += part[i];
+        stats.samples += st.samples; stats.closest_rays += st.closest_rays; stats.shadow_rays += st.shadow_rays;
+        stats.shadow_rays_traced += st.shadow_rays_traced; stats.contact_rays += st.contact_rays; stats.nan_samples += st.nan_samples;
+        stats.iterations += st.iterations; stats.kernel_launches += st.kernel_launches;
+        if (end >= spp) break;
+    }
     int status = 0;
     if (rc != CRAY_OK) {
         std::fprintf(stderr, "[ERROR] %s\n", cray_last_error());

@@ -158,3 +158,21 @@ def test_compiled_cli_renders_the_same_film_as_the_library(tmp_path):
     out2 = tmp_path / "out2.exr"
     res = subprocess.run([CLI, "-s", str(scene_path), "--output", str(out2), "--spp", "2", "--mode", "f32", "--preview"], capture_output=True, text=True)
     assert res.returncode == 0 and read_exr(out2).shape == (40, 64, 3)
+
+
+@pytest.mark.gpu
+def test_both_command_lines_split_long_sample_ranges(tmp_path):
+    """One render call takes at most 2^32 - 1 samples; the command lines render a longer frame as several sample ranges and add
+    the film sums (here forced by --samples-per-call: 7 samples as 3 + 3 + 1)."""
+    text = scenes.simple(num_samples=7, width=64, height=40)
+    scene_path = tmp_path / "simple_small.cry"
+    scene_path.write_text(text)
+    whole, split, py_split = tmp_path / "whole.exr", tmp_path / "split.exr", tmp_path / "py_split.exr"
+    for out, extra in ((whole, []), (split, ["--samples-per-call", "3"])):
+        res = subprocess.run([CLI, "--scene", str(scene_path), "--output", str(out), "--seed", "2"] + extra, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+    assert cli_main(["--scene", str(scene_path), "--output", str(py_split), "--seed", "2", "--samples-per-call", "3"]) == 0
+    a, b, p = read_exr(whole), read_exr(split), read_exr(py_split)
+    # (each range's film is rounded to f32 before the ranges are added)
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-6) and np.allclose(a, p, rtol=1e-5, atol=1e-6)
+    assert not np.array_equal(a, read_exr(split) * 0)   # a real image
