@@ -107,5 +107,30 @@ def test_tree_walks_equal_a_loop_over_every_primitive(name):
     hit = want_prim != NO_HIT
     assert np.array_equal(hits["t"][hit], want_t[hit])
     assert np.array_equal(orc.intersects(rays), hit)
+    # the rest of PrimitiveIntersection for the triangle hits (shape.rs:247-258): location, interpolated normal, uv
+    d = hs.desc
+    hits2, surf = orc.intersect(rays, surface=True)
+    assert np.array_equal(hits2["prim"], want_prim)
+    tri = np.ctypeslib.as_array(np.ctypeslib.ctypes.cast(d.triangles, np.ctypeslib.ctypes.POINTER(np.ctypeslib.ctypes.c_double)), shape=(d.n_triangles, 24))
+    checked = 0
+    for r in np.flatnonzero(hit):
+        p = d.primitives[int(want_prim[r])]
+        if p.shape_kind != 1:
+            continue
+        v0, e1, e2, n0, n01, n02 = (tri[p.shape_index, 3 * k:3 * k + 3] for k in range(6))
+        uv0, uv01, uv02 = (tri[p.shape_index, 18 + 2 * k:20 + 2 * k] for k in range(3))
+        ro, rd = rays["origin"][r], rays["direction"][r]
+        P = cross(rd, e2)
+        den = dot(P, e1)
+        T = ro - v0
+        u = dot(P, T) / den
+        v = dot(cross(T, e1), rd) / den
+        n = n0 + n01 * u + n02 * v
+        n = n / np.sqrt(dot(n, n))
+        assert np.array_equal(surf["location"][r], ro + rd * want_t[r]) and np.array_equal(surf["normal"][r], n), r
+        assert np.array_equal(surf["uv"][r], uv0 + uv01 * u + uv02 * v), r
+        assert (hits2["u"][r], hits2["v"][r]) == (u, v)
+        checked += 1
+    assert checked > 30
     assert 0.2 < hit.mean() < 0.98, hit.mean()
     orc.close()
